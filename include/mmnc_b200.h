@@ -1,0 +1,222 @@
+/*
+ * mmnc_b200 — C ABI of the B200-native rate path for the ScaleHyperprior codecs of
+ * narekvslife/multi-modal-neural-compression.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its rate path sits behind
+ * CompressAI 1.2.4's Python modules and two pybind11 modules.  Every entry point
+ * below names the reference call site and the CompressAI interface it replaces.  Conventions:
+ *
+ *   - extern "C", plain pointers and sizes; no torch / C++ types in any signature;
+ *   - every pointer is a DEVICE pointer unless its name ends in `_h`;
+ *   - tensors are dense, row-major ("NCHW-contiguous"): (B, C, S) means B images, C channels, S = H*W;
+ *   - the caller owns and pre-allocates every buffer; the library keeps no persistent device memory;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises;
+ *   - return value: 0 = ok, negative = MMNC_ERR_* (message via mmnc_last_error()); never throws;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns MMNC_ERR_CUDA.
+ *
+ * Reference files are cited relative to /root/reference/src/models/ (mtc.py = multi_task_compressor.py).
+ */
+#ifndef MMNC_B200_H
+#define MMNC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMNC_OK 0
+#define MMNC_ERR_INVALID (-1)     /* bad argument (shape, mode, null pointer) */
+#define MMNC_ERR_CUDA (-2)        /* CUDA runtime error (also: no device) */
+#define MMNC_ERR_UNSUPPORTED (-3) /* valid request outside what the kernels cover */
+
+#define MMNC_EB_PARAMS_PER_CHANNEL 58 /* filters (3,3,3,3): 33 matrix + 13 bias + 12 factor */
+
+/* means_mode for the quantise family */
+#define MMNC_MEANS_NONE 0
+#define MMNC_MEANS_PER_CHANNEL 1 /* means has C entries (EntropyBottleneck medians) */
+#define MMNC_MEANS_FULL 2        /* means has the shape of the input */
+
+/* noise_mode for the forward kernels */
+#define MMNC_QUANT_DEQUANTIZE 0  /* eval: round_half_even(x - m) + m */
+#define MMNC_QUANT_NOISE_PHILOX 1 /* train: x + U(-1/2,1/2) from Philox4x32-10(seed, element index + offset) */
+#define MMNC_QUANT_NOISE_GIVEN 2  /* train (test hook): x + noise[i] read from memory */
+#define MMNC_QUANT_IDENTITY 3     /* input is already quantised: v = x */
+
+/* likelihood_form for the EntropyBottleneck (SURVEY.md A.3 version switch) */
+#define MMNC_EB_FORM_SIGN 0  /* CompressAI 1.2.x: |sigmoid(s*up) - sigmoid(s*lo)|, s = -sign(lo+up) */
+#define MMNC_EB_FORM_PLAIN 1 /* later releases: sigmoid(up) - sigmoid(lo) */
+
+/* precision of the GDN channel contraction */
+#define MMNC_GDN_FP32 0  /* SIMT fp32 FMA */
+#define MMNC_GDN_TF32 1  /* tcgen05 kind::tf32, single pass */
+#define MMNC_GDN_3XTF32 2 /* tcgen05 kind::tf32, hi/lo split (fp32-class accuracy) */
+#define MMNC_GDN_AUTO 3  /* library picks: tensor cores where the shape allows, SIMT otherwise */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Library state
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_version(void);
+const char *mmnc_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
+uint64_t mmnc_launch_count(void);
+int mmnc_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a2) EntropyModel.quantize — CompressAI entropy_models.EntropyModel.quantize(inputs, mode, means),
+ *      reached from EB/GC forward and compress (mtc.py:495, 509).
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_quantize_noise(const float *x, int64_t n, int noise_mode, const float *noise, uint64_t seed,
+                        uint64_t offset, float *out, void *stream);
+int mmnc_quantize_dequantize(const float *x, int64_t B, int64_t C, int64_t S, const float *means, int means_mode,
+                             float *out, void *stream);
+int mmnc_quantize_symbols(const float *x, int64_t B, int64_t C, int64_t S, const float *means, int means_mode,
+                          int32_t *symbols, void *stream);
+/* EntropyModel.dequantize(symbols, means): float(symbols) + means */
+int mmnc_dequantize_symbols(const int32_t *symbols, int64_t B, int64_t C, int64_t S, const float *means,
+                            int means_mode, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a3) EntropyBottleneck.forward / _likelihood / _logits_cumulative (+ LowerBound floor) — mtc.py:495.
+ *   x, out, lik : (B, C, S).  params : (C, 58) RAW parameters packed per channel in the order
+ *     matrix0[3x1] bias0[3] factor0[3] | matrix1[3x3] bias1[3] factor1[3] | matrix2 .. | matrix3 .. |
+ *     matrix4[1x3] bias4[1]          (row-major matrices; softplus / tanh are applied inside the kernel).
+ *   medians : (C).  lnsum : (C) fp32, ACCUMULATED (+=) with sum over (b, s) of ln(lik) — caller zeroes; may be
+ *   NULL.  noise / seed / offset per noise_mode.  likelihood_bound <= 0 disables the floor.
+ * backward: given saved `out`, upstream g_out / g_lik (either may be NULL) and g_lnsum (C, may be NULL; the
+ *   gradient of a loss that consumed lnsum), writes g_x (B, C, S) and ACCUMULATES g_params (C, 58) (caller zeroes).
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_eb_forward(const float *x, int64_t B, int64_t C, int64_t S, const float *params, const float *medians,
+                    int noise_mode, const float *noise, uint64_t seed, uint64_t offset, float likelihood_bound,
+                    int likelihood_form, float *out, float *lik, float *lnsum, void *stream);
+int mmnc_eb_backward(const float *out, int64_t B, int64_t C, int64_t S, const float *params, const float *g_out,
+                     const float *g_lik, const float *g_lnsum, float likelihood_bound, int likelihood_form,
+                     float *g_x, float *g_params, void *stream);
+/* _logits_cumulative on v: (C, L) -> logits (C, L), parameters detached (EntropyBottleneck.update / loss) */
+int mmnc_eb_logits(const float *v, int64_t C, int64_t L, const float *params, float *logits, void *stream);
+/* (a4) EntropyBottleneck.loss() — mtc.py:386-387: loss = sum |F_c(quantiles) - target|; writes the scalar
+ * loss (ACCUMULATED, caller zeroes) and d loss / d quantiles (C, 3) in one launch (parameters detached). */
+int mmnc_eb_aux_loss(const float *quantiles, int64_t C, const float *params, const float *target3, float *loss,
+                     float *g_quantiles, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a5) GaussianConditional.forward / _likelihood (+ LowerBound on scales and on the likelihood) — mtc.py:495.
+ *   y : (B, C, Sy); scales, lik : (B, C, Ss) with Sy == Ss, or Sy == 1 (torch broadcasting, the shape the
+ *   reference actually produces: y (B,M,1,1) against scales (B,M,4,4)).
+ *   means : NULL or (B, C, Sy).  y_hat : (B, C, Sy).  lnsum : (C) accumulated sum of ln(lik), may be NULL.
+ * backward writes g_y (B, C, Sy) and g_scales (B, C, Ss); g_yhat / g_lik / g_lnsum may each be NULL.
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_gc_forward(const float *y, const float *scales, const float *means, int64_t B, int64_t C, int64_t Sy,
+                    int64_t Ss, int noise_mode, const float *noise, uint64_t seed, uint64_t offset,
+                    float scale_bound, float likelihood_bound, float *y_hat, float *lik, float *lnsum,
+                    void *stream);
+int mmnc_gc_backward(const float *y_hat, const float *scales, const float *means, int64_t B, int64_t C,
+                     int64_t Sy, int64_t Ss, const float *g_yhat, const float *g_lik, const float *g_lnsum,
+                     float scale_bound, float likelihood_bound, float *g_y, float *g_scales, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a6, a13) per-channel sum of ln(likelihood) for a likelihood tensor that did not come with one
+ *   (MultiTaskCompressor._bits_per_pixel, mtc.py:278-293).  lik (B, C, S) -> lnsum (C), accumulated.
+ *   backward: g_lik = g_lnsum[c] / lik.
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_lnsum_forward(const float *lik, int64_t B, int64_t C, int64_t S, float *lnsum, void *stream);
+int mmnc_lnsum_backward(const float *lik, int64_t B, int64_t C, int64_t S, const float *g_lnsum, float *g_lik,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a7) distortion terms of the multi-task RD loss — MultiTaskCompressor.reconstruction_loss, mtc.py:223-255.
+ *   kind 0: sum (a-b)^2, kind 1: sum |a-b|.  `out` (one float) is ACCUMULATED with scale * sum.
+ *   backward: g_a = (*g_scalar) * scale * d/da, with g_scalar a device scalar (no host sync).
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_distortion_forward(const float *a, const float *b, int64_t n, int kind, float scale, float *out,
+                            void *stream);
+int mmnc_distortion_backward(const float *a, const float *b, int64_t n, int kind, float scale,
+                             const float *g_scalar, float *g_a, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a6, a7) RD-loss epilogue — multitask_compression_loss (mtc.py:302-357, mixed_latent.py:70-118,
+ *   shared_latent.py:118-147), multitask_reconstruction_loss (mtc.py:257-276), UncertaintyWeightingStrategy
+ *   (loss_balancing.py:31-54), loss = lmbda * rec + comp (mtc.py:437).  One launch, one block.
+ *   lnsum_y (M), lnsum_z (N): per-channel sums of ln(lik).  group_of_channel (M) int32: y channel -> rate group
+ *   index in [0, n_groups) or -1 for channels that carry no rate term (Disjoint's orphaned channels).
+ *   group_inv_pixels (n_groups): 1 / (B*H*W) of the task the group is normalised by; group_weight (n_groups):
+ *   weight of the group's bpp in the total (1/T).  z_inv_pixels, z_weight likewise for z.
+ *   task_losses (T): raw distortion per task; log_vars (T) or NULL (no weighting, SingleTask).
+ *   outputs: scalars[0]=loss, [1]=rec, [2]=comp, [3]=z_bpp, [4..4+n_groups)=group bpp, then T weighted task
+ *   losses.  Gradients of `loss`: g_lnsum_y (M), g_lnsum_z (N), g_task_losses (T), g_log_vars (T).
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_rd_epilogue(const float *lnsum_y, int64_t M, const float *lnsum_z, int64_t N,
+                     const int32_t *group_of_channel, int n_groups, const float *group_inv_pixels,
+                     const float *group_weight, float z_inv_pixels, float z_weight, const float *task_losses,
+                     int T, const float *log_vars, float lmbda, float *scalars, float *g_lnsum_y,
+                     float *g_lnsum_z, float *g_task_losses, float *g_log_vars, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a8) GDN / IGDN — compressai.layers.GDN.forward, sites mtc.py:146-172, disjoint_latent.py:150-154 and the
+ *   backbone's g_a / g_s.  y_i = x_i * (beta_i + sum_j gamma_ij x_j^2)^(-1/2) (GDN) or ^(+1/2) (inverse).
+ *   x, y, g, dx : (B, C, HW).  beta (C), gamma (C, C): EFFECTIVE (already re-parametrised) values.
+ *   backward: dx, and d beta (C) / d gamma (C, C) w.r.t. the effective values (OVERWRITTEN, not accumulated).
+ *   workspace: device scratch of at least mmnc_gdn_backward_workspace_bytes(B, C, HW, precision) bytes.
+ *   precision: MMNC_GDN_*.  The reparametrisation (NonNegativeParametrizer + LowerBound) is below.
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_gdn_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta, const float *gamma,
+                     int inverse, int precision, float *y, void *stream);
+size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int precision);
+int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
+                      const float *gamma, int inverse, int precision, float *dx, float *dbeta, float *dgamma,
+                      void *workspace, size_t workspace_bytes, void *stream);
+/* NonNegativeParametrizer.forward: out = max(p, bound)^2 - pedestal, and its backward with LowerBound's
+ * custom gradient (pass when p >= bound or when the incoming gradient is negative). */
+int mmnc_nonneg_reparam_forward(const float *p, int64_t n, float bound, float pedestal, float *out, void *stream);
+int mmnc_nonneg_reparam_backward(const float *p, const float *g_out, int64_t n, float bound, float *g_p,
+                                 void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a9) compressai._CXX.pmf_to_quantized_cdf(pmf: List[float], precision) -> List[int]  — HOST function
+ *   (called once per table row from EntropyBottleneck.update / GaussianConditional.update, reference call site
+ *   mtc.py:486-489, off the per-step path).  pmf_h: n floats; cdf_h: n + 1 uint32, strictly increasing,
+ *   cdf_h[0] = 0, cdf_h[n] = 2^precision.  Integer arithmetic identical to CompressAI's (bit-exact tables).
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_pmf_to_quantized_cdf_h(const float *pmf_h, int n, int precision, uint32_t *cdf_h);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a10) GaussianConditional.build_indexes — mtc.py:545 and inside ScaleHyperprior.compress (mtc.py:509):
+ *   idx = (len-1) - #{ t in table[:-1] : max(scale, bound) <= t }.
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_build_indexes(const float *scales, int64_t n, const float *scale_table, int table_len, float scale_bound,
+                       int32_t *indexes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * (a11, a12) batched rANS — replaces compressai.ans.RansEncoder.encode_with_indexes /
+ *   RansDecoder.decode_with_indexes (pybind11, one stream per call) reached from mtc.py:509, 543, 546.
+ *   Bit-exact with CompressAI's format: one 64-bit-state stream per image, 32-bit words, 16-bit probabilities,
+ *   4-bit bypass escape, native-endian bytes.  One stream per row of `symbols`.
+ *
+ *   symbols (n_streams, n_sym) int32; indexes same shape, or NULL with channel_period > 0 meaning
+ *   index = (position / channel_period) % n_cdfs (EntropyBottleneck: channel id).
+ *   cdf (n_cdfs, cdf_stride) int32 = `_quantized_cdf`; cdf_sizes = `_cdf_length`; offsets = `_offset`.
+ *   encode: `staging` is scratch of n_streams*n_sym*8 bytes; `slabs` (n_streams, slab_words) uint32 with
+ *   slab_words >= mmnc_rans_slab_words(n_sym); nbytes (n_streams) int32 receives each stream's byte count
+ *   (a negative value flags a malformed input for that stream).  The stream's bytes are the LAST nbytes[i]
+ *   bytes of its slab.  mmnc_rans_compact packs them back to back: offsets (n_streams + 1) int64 exclusive
+ *   scan, packed = concatenation.
+ * ------------------------------------------------------------------------------------------------------- */
+int64_t mmnc_rans_slab_words(int64_t n_sym);
+int mmnc_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int64_t channel_period,
+                           int64_t n_streams, int64_t n_sym, const int32_t *cdf, int n_cdfs, int cdf_stride,
+                           const int32_t *cdf_sizes, const int32_t *offsets, void *staging, uint32_t *slabs,
+                           int64_t slab_words, int32_t *nbytes, void *stream);
+int mmnc_rans_compact(const uint32_t *slabs, int64_t slab_words, const int32_t *nbytes, int64_t n_streams,
+                      int64_t *offsets, uint8_t *packed, int64_t packed_capacity, void *stream);
+/* decode: packed bytes + offsets (n_streams + 1) as produced above (each stream 4-byte aligned is NOT
+ * required).  status (n_streams) int32: 0 ok, negative = stream overrun / malformed. */
+int mmnc_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, const int32_t *indexes,
+                           int64_t channel_period, int64_t n_streams, int64_t n_sym, const int32_t *cdf,
+                           int n_cdfs, int cdf_stride, const int32_t *cdf_sizes, const int32_t *cdf_offsets,
+                           int32_t *symbols, int32_t *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMNC_B200_H */

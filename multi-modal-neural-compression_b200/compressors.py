@@ -1,0 +1,479 @@
+"""Host-side mirror of the reference's four multi-task compressors (same class names, constructor arguments and
+method names), built on this package's kernels instead of CompressAI + ~150 torch launches per step.
+
+  MultiTaskCompressor                 /root/reference/src/models/multi_task_compressor.py:27-549
+  MultiTaskMixedLatentCompressor      /root/reference/src/models/mixed_latent.py:15-162          (-m 2)
+  MultiTaskDisjointLatentCompressor   /root/reference/src/models/disjoint_latent.py:14-194       (-m 3)
+  MultiTaskSharedLatentCompressor     /root/reference/src/models/shared_latent.py:9-162          (-m 4)
+  SingleTaskCompressor                /root/reference/src/models/single_task_compressor.py:13-55 (-m 1)
+  UncertaintyWeightingStrategy        /root/reference/src/loss_balancing.py:21-54
+
+Lightning is replaced by plain `nn.Module` + explicit optimizers (the training harness is out of scope,
+SURVEY.md section 2 row 8); `training_step` keeps the reference's two-optimizer order (mtc.py:448-466).
+What is different by design: the rate term is computed from the per-channel sums of ln(likelihood) that the
+likelihood kernels already reduced, and the whole scalar part of the RD loss (group bpp, uncertainty weighting,
+lmbda * rec + comp, and all their gradients) is ONE launch (`mmnc_rd_epilogue`).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .layers import GDN, conv, deconv
+from .models import ScaleHyperprior, get_scale_table
+
+# /root/reference/src/datasets/task_configs.py:7-33
+task_parameters = {
+    "depth_euclidean": {"in_channels": 1, "out_channels": 1, "loss_function": "mse"},
+    "rgb": {"in_channels": 3, "out_channels": 3, "loss_function": "mse"},
+    "semantic": {"in_channels": 1, "out_channels": 17, "loss_function": "cross-entropy"},
+    "normal": {"in_channels": 3, "out_channels": 3, "loss_function": "mse"},
+    "mono": {"in_channels": 1, "out_channels": 1, "loss_function": "mse"},
+}
+
+
+class DummyModule(nn.Module):
+    """/root/reference/src/utils.py:56-61"""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+
+    def forward(self, x):
+        return x
+
+
+class NoWeightingStrategy(DummyModule):
+    """/root/reference/src/loss_balancing.py:15-18"""
+
+
+class UncertaintyWeightingStrategy(nn.Module):
+    """exp(-s_t) L_t + s_t (zeroed where L_t == 0).  The arithmetic runs inside `mmnc_rd_epilogue`; the stand-alone
+    `forward` keeps the reference's dict-in / dict-out behaviour for callers that use it directly."""
+
+    def __init__(self, num_tasks: int):
+        super().__init__()
+        self.log_vars = nn.Parameter(torch.zeros(num_tasks))
+
+    def forward(self, task_losses: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        losses = torch.stack(list(task_losses.values()))
+        weighted = (torch.exp(-self.log_vars) * losses + self.log_vars) * (losses != 0.0)
+        out = dict(task_losses)
+        out.update(zip(out, weighted))
+        return out
+
+
+class LikelihoodDict(dict):
+    """{"y": ..., "z": ...} like CompressAI's, plus `.log_sums` = per-channel sums of ln(likelihood)."""
+
+    log_sums: Optional[Dict[str, torch.Tensor]] = None
+
+
+class MultiTaskCompressor(nn.Module):
+    def __init__(self, compressor_backbone_class: type, tasks: Tuple[str], input_channels: Tuple[int],
+                 output_channels: Optional[Tuple[int]] = None, latent_channels: int = 128, conv_channels: int = 100,
+                 lmbda: float = 1, learning_rate_main=1e-5, learning_rate_aux=1e-3, **kwargs):
+        super().__init__()
+        self.compressor_backbone_class = compressor_backbone_class or ScaleHyperprior
+        self.tasks = tuple(tasks)
+        self.n_tasks = len(self.tasks)
+        self.input_channels = tuple(input_channels)
+        self.output_channels = tuple(output_channels) if output_channels is not None else tuple(
+            task_parameters[t]["out_channels"] for t in self.tasks)
+        assert self.n_tasks == len(self.input_channels)
+        self.latent_channels = latent_channels
+        self.conv_channels = conv_channels
+        self.lmbda = lmbda
+        self.learning_rate_main = learning_rate_main
+        self.learning_rate_aux = learning_rate_aux
+        self.kwargs = kwargs
+        self.model: nn.ModuleDict = self._build_model()
+        self.loss_balancer = UncertaintyWeightingStrategy(self.n_tasks)
+        self._cache: Dict[tuple, tuple] = {}
+        self._optimizers = None
+        self.grad_sync = None  # set by parallel.DataParallel: called between backward() and optimizer.step()
+
+    def get_model_name(self):
+        return self.__class__.__name__
+
+    def _get_number_of_pixels(self, x_hats: Dict[str, torch.Tensor], task: str) -> int:
+        B, _, H, W = x_hats[task].shape
+        return B * H * W
+
+    # ------------------------------------------------------------------ topology (mtc.py:109-193)
+    def _build_heads(self, input_channels: Union[Sequence[int], int],
+                     output_channels_per_head: Union[Sequence[int], int], is_deconv=False) -> nn.ModuleList:
+        T = self.n_tasks
+        cin = [input_channels] * T if isinstance(input_channels, int) else list(input_channels)
+        cout = [output_channels_per_head] * T if isinstance(output_channels_per_head, int) else list(
+            output_channels_per_head)
+        assert len(cin) == T and len(cout) == T
+        heads = []
+        for ic, oc in zip(cin, cout):
+            if is_deconv:
+                m = ic // 2
+                seq = [deconv(ic, m), GDN(m, inverse=True), conv(m, m, kernel_size=3, stride=1), GDN(m, inverse=True),
+                       deconv(m, m), GDN(m, inverse=True), conv(m, m, kernel_size=3, stride=1), GDN(m, inverse=True),
+                       deconv(m, oc), GDN(oc, inverse=True), deconv(oc, oc), GDN(oc, inverse=True),
+                       conv(oc, oc, kernel_size=3, stride=1)]
+            else:
+                m = oc // 2
+                seq = [conv(ic, m, kernel_size=3, stride=1), GDN(m), conv(m, oc), GDN(oc)]
+                for _ in range(4):
+                    seq += [conv(oc, oc), GDN(oc)]
+            heads.append(nn.Sequential(*seq))
+        return nn.ModuleList(heads)
+
+    def _build_compression_backbone(self, input_channels: int, latent_channels: int) -> nn.Module:
+        model = self.compressor_backbone_class(N=input_channels, M=latent_channels, **self.kwargs)
+        model.g_a[0] = conv(input_channels, input_channels)
+        model.g_s[-1] = deconv(input_channels, input_channels)
+        return model
+
+    def _build_model(self) -> nn.ModuleDict:
+        raise NotImplementedError()
+
+    # ------------------------------------------------------------------ forward (mtc.py:200-221, 491-505)
+    def forward_input_heads(self, batch) -> torch.Tensor:
+        return torch.concat([self.model["input_heads"][i](batch[t]) for i, t in enumerate(self.tasks)], dim=1)
+
+    def forward_output_heads(self, stacked_latent_values):
+        raise NotImplementedError()
+
+    def forward(self, batch):
+        out = self.model["compressor"](self.forward_input_heads(batch))
+        lik = LikelihoodDict(out["likelihoods"])
+        lik.log_sums = out.get("log_likelihood_sums")
+        return self.forward_output_heads(out["x_hat"]), lik
+
+    # ------------------------------------------------------------------ rate groups (a13)
+    def _rate_groups(self):
+        """-> (channel -> group id list (M, -1 = no rate term), [task index normalising each group], group names)."""
+        raise NotImplementedError()
+
+    def _group_tables(self, x_hats, device):
+        px = tuple(self._get_number_of_pixels(x_hats, t) for t in self.tasks)
+        key = (px, str(device))
+        if key not in self._cache:
+            chan, norm_task, names = self._rate_groups()
+            inv = torch.tensor([1.0 / px[t] for t in norm_task], dtype=torch.float32, device=device)
+            w = torch.full((len(norm_task),), 1.0 / self.n_tasks, dtype=torch.float32, device=device)
+            self._cache[key] = (torch.tensor(chan, dtype=torch.int32, device=device), inv, w, 1.0 / px[0], names)
+        return self._cache[key]
+
+    def _log_sums(self, likelihoods):
+        sums = getattr(likelihoods, "log_sums", None)
+        if sums is None or sums.get("y") is None or sums.get("z") is None:
+            sums = {k: ops.channel_log_likelihood_sums(v) for k, v in likelihoods.items()}
+        return sums
+
+    # ------------------------------------------------------------------ distortion (mtc.py:223-276)
+    def reconstruction_loss(self, x_hat, x, loss_type: str = "mse") -> torch.Tensor:
+        if loss_type in ("mse", "l1"):
+            return ops.distortion(x_hat, x, loss_type)
+        if loss_type == "cross-entropy":
+            return F.cross_entropy(input=x_hat, target=x.squeeze(1).long(), reduction="mean")
+        if loss_type == "ms-ssim":
+            raise NotImplementedError("ms-ssim not implemented yet")
+        raise NotImplementedError("reconstruction_loss_type should be one of [mse, ms-ssim]")
+
+    def _task_losses(self, x, x_hats, log_dir, logs):
+        vals = []
+        for task in self.tasks:
+            name = task_parameters[task]["loss_function"]
+            vals.append(self.reconstruction_loss(x_hat=x_hats[task], x=x[task], loss_type=name))
+            logs[f"{log_dir}/{task}/{name}"] = vals[-1].detach()
+        return torch.stack(vals)
+
+    def _log_vars(self):
+        return getattr(self.loss_balancer, "log_vars", None)
+
+    # ------------------------------------------------------------------ fused RD loss (a6 + a7 + mtc.py:437)
+    def rate_distortion_loss(self, batch, x_hats, likelihoods, log_dir: str):
+        """loss = lmbda * sum_t w_t(L_t) + comp, with every scalar the reference logs; one epilogue launch."""
+        logs: Dict[str, torch.Tensor] = {}
+        task_losses = self._task_losses(batch, x_hats, log_dir, logs)
+        sums = self._log_sums(likelihoods)
+        chan, inv, w, z_inv, names = self._group_tables(x_hats, task_losses.device)
+        loss, s = ops.rd_epilogue(sums["y"], sums["z"], task_losses, self._log_vars(), chan, inv, w, z_inv,
+                                  1.0 / self.n_tasks, self.lmbda)
+        G = inv.numel()
+        logs[f"{log_dir}/rec_loss"], logs[f"{log_dir}/compression_loss"], logs[f"{log_dir}/loss"] = s[1], s[2], s[0]
+        self._compression_logs(logs, log_dir, names, s[4:4 + G], s[3])
+        if self._log_vars() is not None:
+            for i, task in enumerate(self.tasks):
+                logs[f"uncertainty-weight/{task}"] = self.loss_balancer.log_vars[i].detach()
+        return loss, logs
+
+    def _compression_logs(self, logs, log_dir, names, group_bpp, z_bpp):
+        for i, name in enumerate(names):
+            logs[f"{log_dir}/{name}/compression_loss"] = group_bpp[i] + z_bpp
+
+    # reference-shaped entry points (each returns (value, logs)); same kernels, partial epilogues
+    def multitask_reconstruction_loss(self, x, x_hats, log_dir: str):
+        logs: Dict[str, torch.Tensor] = {}
+        task_losses = self._task_losses(x, x_hats, log_dir, logs)
+        dev = task_losses.device
+        empty = torch.zeros(0, dtype=torch.float32, device=dev)
+        rec, _ = ops.rd_epilogue(empty, empty, task_losses, self._log_vars(),
+                                 torch.zeros(0, dtype=torch.int32, device=dev), empty, empty, 0.0, 0.0, 1.0)
+        if self._log_vars() is not None:
+            for i, task in enumerate(self.tasks):
+                logs[f"uncertainty-weight/{task}"] = self.loss_balancer.log_vars[i].detach()
+        return rec, logs
+
+    def _bits_per_pixel(self, likelihoods: torch.Tensor, num_pixels) -> torch.Tensor:
+        return ops.channel_log_likelihood_sums(likelihoods).sum() / (-torch.log(torch.tensor(2.0))) / num_pixels
+
+    def multitask_compression_loss(self, all_likelihoods, x_hats, log_dir: str):
+        logs: Dict[str, torch.Tensor] = {}
+        sums = self._log_sums(all_likelihoods)
+        dev = sums["y"].device
+        chan, inv, w, z_inv, names = self._group_tables(x_hats, dev)
+        loss, s = ops.rd_epilogue(sums["y"], sums["z"], torch.zeros(0, dtype=torch.float32, device=dev), None, chan, inv,
+                                  w, z_inv, 1.0 / self.n_tasks, 0.0)
+        self._compression_logs(logs, log_dir, names, s[4:4 + inv.numel()], s[3])
+        return loss, logs
+
+    # ------------------------------------------------------------------ optimisation (mtc.py:386-418)
+    def auxiliary_loss(self):
+        return self.model["compressor"].entropy_bottleneck.loss()
+
+    def get_main_parameters(self):
+        return [p for n, p in self.model.named_parameters() if not n.endswith(".quantiles")]
+
+    def get_auxiliary_parameters(self):
+        return [p for n, p in self.model.named_parameters() if n.endswith(".quantiles")]
+
+    def configure_optimizers(self, total_steps: int = 1000):
+        fused = next(self.parameters()).is_cuda
+        main = torch.optim.Adam(self.get_main_parameters() + list(self.loss_balancer.parameters()),
+                                lr=self.learning_rate_main, fused=fused)
+        sch = torch.optim.lr_scheduler.CosineAnnealingLR(main, T_max=total_steps, eta_min=1e-8)
+        aux = torch.optim.Adam(self.get_auxiliary_parameters(), lr=self.learning_rate_aux, fused=fused)
+        self._optimizers = (main, aux, sch)
+        return {"optimizer": main, "lr_scheduler": {"scheduler": sch}}, {"optimizer": aux}
+
+    def optimizers(self):
+        if self._optimizers is None:
+            self.configure_optimizers()
+        return self._optimizers[0], self._optimizers[1]
+
+    def lr_schedulers(self):
+        return self._optimizers[2]
+
+    # ------------------------------------------------------------------ steps (mtc.py:420-483)
+    def _step(self, batch, is_train: bool):
+        log_dir = "train" if is_train else "val"
+        x_hats, likelihoods = self.forward(batch)
+        loss, log_dict = self.rate_distortion_loss(batch, x_hats, likelihoods, log_dir)
+        if is_train:
+            main_opt, aux_opt = self.optimizers()
+            main_opt.zero_grad(set_to_none=False)
+            loss.backward()
+            if self.grad_sync is not None:
+                self.grad_sync()
+            main_opt.step()
+            aux_loss = self.auxiliary_loss()
+            log_dict[f"{log_dir}/aux_loss"] = aux_loss.detach()
+            aux_opt.zero_grad(set_to_none=False)
+            aux_loss.backward()
+            aux_opt.step()
+            self.lr_schedulers().step()
+        self.last_logs = log_dict
+        return loss
+
+    def training_step(self, batch, batch_idx: int = 0):
+        return self._step(batch, is_train=True)
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx: int = 0):
+        return self._step(batch, is_train=False)
+
+    # ------------------------------------------------------------------ eval-time coding (mtc.py:486-549)
+    def update_bottleneck_values(self):
+        self.model["compressor"].gaussian_conditional.update_scale_table(get_scale_table())
+        return self.model["compressor"].entropy_bottleneck.update()
+
+    @torch.no_grad()
+    def compress(self, batch, print_info: bool = False):
+        stacked_t = self.forward_input_heads(batch)
+        ans = self.model["compressor"].compress(stacked_t)
+        number_of_bytes = sum(len(s) for latents in ans["strings"] for s in latents)
+        stacked_t_likelihoods = None
+        if print_info:
+            B, _, H, W = batch[self.tasks[0]].shape
+            bpp = number_of_bytes * 8 / B / H / W / self.n_tasks
+            print(f"Number of actual bytes in a string is: {number_of_bytes}, which gives a BPP = {bpp:.3f}")
+            out = self.model["compressor"](stacked_t)
+            stacked_t_likelihoods = LikelihoodDict(out["likelihoods"])
+            stacked_t_likelihoods.log_sums = out.get("log_likelihood_sums")
+            compression_loss, _ = self.multitask_compression_loss(stacked_t_likelihoods, x_hats=batch, log_dir="")
+            print(f"Estimated BPP (compression loss) is: {compression_loss.item():.3f}")
+        return ans, number_of_bytes, stacked_t_likelihoods
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 2
+        c = self.model["compressor"]
+        z_hat = c.entropy_bottleneck.decompress(strings[1], shape)
+        scales_hat = c.h_s(z_hat)
+        indexes = c.gaussian_conditional.build_indexes(scales_hat)
+        y_hat = c.gaussian_conditional.decompress(strings[0], indexes, z_hat.dtype)
+        return self.forward_output_heads(c.g_s(y_hat))
+
+
+class MultiTaskMixedLatentCompressor(MultiTaskCompressor):
+    """All tasks share all M latent channels; every output head sees the whole latent (mixed_latent.py)."""
+
+    def _rate_groups(self):
+        M = self.model["compressor"].M
+        return [0] * M, [0], ["__all__"]
+
+    def _compression_logs(self, logs, log_dir, names, group_bpp, z_bpp):
+        for task in self.tasks:  # mixed_latent.py:108-110: every task reports the full y + z rate
+            logs[f"{log_dir}/{task}/compression_loss"] = group_bpp[0] + z_bpp
+
+    def _get_task_likelihoods(self, likelihoods, task):
+        return likelihoods
+
+    def _build_model(self) -> nn.ModuleDict:
+        model = nn.ModuleDict()
+        model["input_heads"] = self._build_heads(self.input_channels, self.conv_channels)
+        total = self.conv_channels * self.n_tasks
+        model["compressor"] = self._build_compression_backbone(total, self.latent_channels)
+        model["output_heads"] = self._build_heads(total, self.output_channels, is_deconv=True)
+        return model
+
+    def forward_output_heads(self, stacked_latent_values):
+        return {t: self.model["output_heads"][i](stacked_latent_values) for i, t in enumerate(self.tasks)}
+
+
+class SingleTaskCompressor(MultiTaskMixedLatentCompressor):
+    """One task, no loss weighting (single_task_compressor.py:55)."""
+
+    def __init__(self, compressor_backbone_class, tasks, input_channels, latent_channels, conv_channels,
+                 lmbda: float = 1, learning_rate_main=1e-5, learning_rate_aux=1e-3, output_channels=None, **kwargs):
+        assert len(tasks) == 1
+        super().__init__(compressor_backbone_class=compressor_backbone_class, tasks=tasks,
+                         input_channels=input_channels, output_channels=output_channels,
+                         conv_channels=conv_channels, latent_channels=latent_channels, lmbda=lmbda,
+                         learning_rate_main=learning_rate_main, learning_rate_aux=learning_rate_aux, **kwargs)
+        self.loss_balancer = NoWeightingStrategy()
+
+
+class MultiTaskDisjointLatentCompressor(MultiTaskCompressor):
+    """Latent channels sliced per task, g_s removed, four extra deconvs per output head (disjoint_latent.py)."""
+
+    def __init__(self, compressor_backbone_class, tasks, input_channels, output_channels=None, latent_channels=128,
+                 conv_channels=100, lmbda: float = 1, learning_rate_main=1e-5, learning_rate_aux=1e-3, **kwargs):
+        self.latent_channels_per_task = latent_channels // len(tasks)
+        super().__init__(compressor_backbone_class=compressor_backbone_class, tasks=tasks,
+                         input_channels=input_channels, output_channels=output_channels,
+                         conv_channels=conv_channels, latent_channels=latent_channels, lmbda=lmbda,
+                         learning_rate_main=learning_rate_main, learning_rate_aux=learning_rate_aux, **kwargs)
+        if self.latent_channels % self.n_tasks != 0:
+            # disjoint_latent.py:68-75: cosmetic — the backbone was already built with the unrounded count, so
+            # the trailing channels are coded but carry no rate term and feed no decoder
+            self.latent_channels = self.latent_channels_per_task * self.n_tasks
+
+    def _group_width(self) -> int:
+        return self.latent_channels_per_task
+
+    def _rate_groups(self):
+        M, k, T = self.model["compressor"].M, self._group_width(), self.n_tasks
+        chan = [(c // k) if c < k * T else -1 for c in range(M)]
+        return chan, list(range(T)), list(self.tasks)
+
+    def _get_task_channels(self, tensor: torch.Tensor, task: str) -> torch.Tensor:
+        assert tensor.dim() == 4
+        i, k = self.tasks.index(task), self._group_width()
+        return tensor[:, i * k:(i + 1) * k, :, :]
+
+    def _get_task_likelihoods(self, likelihoods, task):
+        return self._get_task_channels(likelihoods["y"], task)
+
+    def _build_heads(self, input_channels, output_channels_per_head, is_deconv=False) -> nn.ModuleList:
+        if not is_deconv:
+            return super()._build_heads(input_channels, output_channels_per_head, is_deconv)
+        w = self.conv_channels // self.n_tasks
+        tails = super()._build_heads(self.conv_channels, output_channels_per_head, is_deconv)
+        heads = nn.ModuleList()
+        for i in range(self.n_tasks):
+            heads.append(nn.Sequential(deconv(input_channels, w), GDN(w, inverse=True), deconv(w, w),
+                                       GDN(w, inverse=True), deconv(w, w), GDN(w, inverse=True),
+                                       deconv(w, self.conv_channels), tails[i]))
+        return heads
+
+    def _head_width(self) -> int:
+        return self.latent_channels_per_task
+
+    def _build_model(self) -> nn.ModuleDict:
+        model = nn.ModuleDict()
+        model["input_heads"] = self._build_heads(self.input_channels, self.conv_channels)
+        total = self.conv_channels * self.n_tasks
+        model["compressor"] = self._build_compression_backbone(total, self.latent_channels)
+        model["compressor"].g_s = DummyModule()
+        model["output_heads"] = self._build_heads(self._head_width(), self.output_channels, is_deconv=True)
+        return model
+
+    def forward_output_heads(self, stacked_latent_values):
+        return {t: self.model["output_heads"][i](self._get_task_channels(stacked_latent_values, t))
+                for i, t in enumerate(self.tasks)}
+
+
+class MultiTaskSharedLatentCompressor(MultiTaskDisjointLatentCompressor):
+    """T task-specific channel groups plus one shared group that every head also reads (shared_latent.py)."""
+
+    def __init__(self, compressor_backbone_class, tasks, input_channels, output_channels=None, latent_channels=192,
+                 conv_channels=128, lmbda: float = 1, learning_rate_main=1e-5, learning_rate_aux=1e-3, **kwargs):
+        n = len(tasks)
+        if latent_channels % (n + 1) != 0:
+            latent_channels = latent_channels // (n + 1) * (n + 1)  # shared_latent.py:34-41
+        self.task_specific_channels_n = latent_channels // (n + 1)
+        super().__init__(compressor_backbone_class=compressor_backbone_class, tasks=tasks,
+                         input_channels=input_channels, output_channels=output_channels,
+                         conv_channels=conv_channels, latent_channels=latent_channels, lmbda=lmbda,
+                         learning_rate_main=learning_rate_main, learning_rate_aux=learning_rate_aux, **kwargs)
+
+    def _group_width(self) -> int:
+        return self.task_specific_channels_n
+
+    def _head_width(self) -> int:
+        return self.task_specific_channels_n * 2
+
+    def _rate_groups(self):
+        M, k, T = self.model["compressor"].M, self._group_width(), self.n_tasks
+        chan = [min(c // k, T) for c in range(M)]  # M == (T + 1) * k; the last group is the shared one
+        return chan, list(range(T)) + [0], list(self.tasks) + ["shared"]
+
+    def _shared_channels(self, tensor: torch.Tensor) -> torch.Tensor:
+        return tensor[:, -self.task_specific_channels_n:, :, :]
+
+    def _get_task_likelihoods(self, likelihoods, task):
+        if task == "shared":
+            return self._shared_channels(likelihoods["y"])
+        return self._get_task_channels(likelihoods["y"], task)
+
+    def forward_output_heads(self, stacked_latent_values):
+        B, _, H, W = stacked_latent_values.shape
+        shared = self._shared_channels(stacked_latent_values)
+        out = {}
+        for i, t in enumerate(self.tasks):
+            own = self._get_task_channels(stacked_latent_values, t)
+            out[t] = self.model["output_heads"][i](torch.stack([own, shared], dim=1).reshape((B, -1, H, W)))
+        return out
+
+
+def build_compressor(model_type: int, tasks: Sequence[str], latent_channels: int, conv_channels: int,
+                     lmbda: float = 1.0, **kw) -> MultiTaskCompressor:
+    """The reference CLI's `-m {1,2,3,4} -t ... -l ... -c ... --lmbda ...` (/root/reference/src/train.py:89-120)."""
+    cls = {1: SingleTaskCompressor, 2: MultiTaskMixedLatentCompressor, 3: MultiTaskDisjointLatentCompressor,
+           4: MultiTaskSharedLatentCompressor}[int(model_type)]
+    cin = tuple(task_parameters[t]["in_channels"] for t in tasks)
+    cout = tuple(task_parameters[t]["out_channels"] for t in tasks)
+    return cls(compressor_backbone_class=ScaleHyperprior, tasks=tuple(tasks), input_channels=cin,
+               output_channels=cout, latent_channels=latent_channels, conv_channels=conv_channels, lmbda=lmbda, **kw)

@@ -1,0 +1,99 @@
+// Library state: version, error slot, launch counter, device query; GDN dispatch between the SIMT and the
+// tensor-core kernels.
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mmnc {
+
+static thread_local char g_error[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        else cudaGetLastError();
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+// gdn_simt.cu
+int gdn_simt_forward(const float *, int64_t, int64_t, int64_t, const float *, const float *, int, float *, cudaStream_t);
+size_t gdn_simt_backward_workspace(int64_t, int64_t, int64_t);
+int gdn_simt_backward(const float *, const float *, int64_t, int64_t, int64_t, const float *, const float *, int,
+                      float *, float *, float *, void *, size_t, cudaStream_t);
+// gdn_tc.cu
+bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW);
+int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const float *, const float *, int, int, float *, cudaStream_t);
+
+}  // namespace mmnc
+
+using namespace mmnc;
+
+extern "C" int mmnc_version(void) { return 100; }
+extern "C" const char *mmnc_last_error(void) { return g_error; }
+extern "C" uint64_t mmnc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" int mmnc_device_sm_count(void) { return sm_count(); }
+
+extern "C" int mmnc_gdn_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta,
+                                const float *gamma, int inverse, int precision, float *y, void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && HW >= 0, "gdn_forward: negative dimension");
+    MMNC_REQUIRE(precision >= 0 && precision <= 3, "gdn_forward: bad precision %d", precision);
+    if (B * C * HW == 0) return MMNC_OK;
+    MMNC_REQUIRE(x && beta && gamma && y, "gdn_forward: null pointer");
+    MMNC_REQUIRE(C <= 8192, "gdn_forward: C = %lld too large", (long long)C);
+    const bool tc_ok = gdn_tc_supported(B, C, HW);
+    if (precision == MMNC_GDN_TF32 || precision == MMNC_GDN_3XTF32) {
+        if (!tc_ok) {
+            set_error("gdn_forward: tensor-core path does not take B=%lld C=%lld HW=%lld", (long long)B, (long long)C,
+                      (long long)HW);
+            return MMNC_ERR_UNSUPPORTED;
+        }
+        return gdn_tc_forward(x, B, C, HW, beta, gamma, inverse, precision, y, as_stream(stream));
+    }
+    if (precision == MMNC_GDN_AUTO && tc_ok)
+        return gdn_tc_forward(x, B, C, HW, beta, gamma, inverse, MMNC_GDN_3XTF32, y, as_stream(stream));
+    return gdn_simt_forward(x, B, C, HW, beta, gamma, inverse, y, as_stream(stream));
+}
+
+extern "C" size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int precision) {
+    (void)precision;
+    if (B <= 0 || C <= 0 || HW <= 0) return 256;
+    return gdn_simt_backward_workspace(B, C, HW);
+}
+
+extern "C" int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
+                                 const float *gamma, int inverse, int precision, float *dx, float *dbeta,
+                                 float *dgamma, void *workspace, size_t workspace_bytes, void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && HW >= 0, "gdn_backward: negative dimension");
+    MMNC_REQUIRE(precision >= 0 && precision <= 3, "gdn_backward: bad precision %d", precision);
+    MMNC_REQUIRE(dbeta && dgamma, "gdn_backward: null pointer");
+    if (B * C * HW == 0) {
+        if (C > 0) {
+            MMNC_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * (size_t)C, as_stream(stream)));
+            MMNC_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * (size_t)(C * C), as_stream(stream)));
+        }
+        return MMNC_OK;
+    }
+    MMNC_REQUIRE(x && g && beta && gamma && dx && workspace, "gdn_backward: null pointer");
+    MMNC_REQUIRE(C <= 8192, "gdn_backward: C = %lld too large", (long long)C);
+    return gdn_simt_backward(x, g, B, C, HW, beta, gamma, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+                             as_stream(stream));
+}

@@ -1,0 +1,216 @@
+// K1 + K2: EntropyBottleneck forward / backward.
+//
+// Replaces CompressAI's EntropyBottleneck.forward chain (quantise -> permute -> 2 x 5-layer per-channel
+// softplus-matrix MLP -> sign trick -> sigmoid difference -> LowerBound -> permute back; ~78 torch launches,
+// reference call site /root/reference/src/models/multi_task_compressor.py:495) with ONE launch per direction.
+//
+// Layout: x is (B, C, S) NCHW-contiguous; the (C, 1, B*S) permutation CompressAI materialises is only an
+// indexing change here.  grid = (C, splits): a block owns one channel, so its 58 transformed parameters sit in
+// shared memory and every lane reads them as broadcasts; threads stride over that channel's B*S elements.
+// Per-channel reductions (sum of ln lik, 58 parameter gradients) are warp shuffles -> shared -> one atomic per
+// block and value.
+#include "common.cuh"
+#include "hd_math.cuh"
+
+namespace mmnc {
+
+constexpr int EB_THREADS = 128;
+
+__device__ __forceinline__ int64_t eb_addr(int64_t e, int64_t c, int64_t C, int64_t S) {
+    const int64_t b = e / S, s = e - b * S;
+    return (b * C + c) * S + s;
+}
+
+__global__ void __launch_bounds__(EB_THREADS)
+eb_forward_kernel(const float *__restrict__ x, int64_t B, int64_t C, int64_t S, const float *__restrict__ params,
+                  const float *__restrict__ medians, int noise_mode, const float *__restrict__ noise,
+                  uint64_t seed, uint64_t offset, float bound, int form, float *__restrict__ out,
+                  float *__restrict__ lik, float *__restrict__ lnsum) {
+    __shared__ float P[EB_NP];
+    __shared__ float red[32];
+    const int64_t c = blockIdx.x;
+    if (threadIdx.x < EB_NP) P[threadIdx.x] = eb_transform(threadIdx.x, params[c * EB_NP + threadIdx.x]);
+    __syncthreads();
+    const float med = medians[c];
+    const int64_t n = B * S;
+    float acc = 0.f;
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
+        const int64_t a = eb_addr(e, c, C, S);
+        const float xv = x[a];
+        float v;
+        if (noise_mode == MMNC_QUANT_DEQUANTIZE) v = rintf(xv - med) + med;
+        else if (noise_mode == MMNC_QUANT_NOISE_PHILOX) v = xv + philox_uniform_centered(seed, (uint64_t)a + offset);
+        else if (noise_mode == MMNC_QUANT_NOISE_GIVEN) v = xv + noise[a];
+        else v = xv;
+        const float lower = eb_logits<false>(P, v - 0.5f, nullptr);
+        const float upper = eb_logits<false>(P, v + 0.5f, nullptr);
+        float l = eb_likelihood(lower, upper, form);
+        if (bound > 0.f) l = fmaxf(l, bound);
+        out[a] = v;
+        lik[a] = l;
+        acc += logf(l);
+    }
+    if (lnsum != nullptr) {
+        const float tot = block_sum(acc, red);
+        if (threadIdx.x == 0) atomicAdd(&lnsum[c], tot);
+    }
+}
+
+__global__ void __launch_bounds__(EB_THREADS)
+eb_backward_kernel(const float *__restrict__ outv, int64_t B, int64_t C, int64_t S,
+                   const float *__restrict__ params, const float *__restrict__ g_out,
+                   const float *__restrict__ g_lik, const float *__restrict__ g_lnsum, float bound, int form,
+                   int train, float *__restrict__ g_x, float *__restrict__ g_params) {
+    __shared__ float P[EB_NP];
+    __shared__ float Praw[EB_NP];
+    __shared__ float red[EB_THREADS / 32][EB_NP];
+    const int64_t c = blockIdx.x;
+    if (threadIdx.x < EB_NP) {
+        const float raw = params[c * EB_NP + threadIdx.x];
+        Praw[threadIdx.x] = raw;
+        P[threadIdx.x] = eb_transform(threadIdx.x, raw);
+    }
+    __syncthreads();
+    const float gls = (g_lnsum != nullptr) ? g_lnsum[c] : 0.f;
+    const int64_t n = B * S;
+    float gP[EB_NP];
+#pragma unroll
+    for (int k = 0; k < EB_NP; ++k) gP[k] = 0.f;
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
+        const int64_t a = eb_addr(e, c, C, S);
+        const float v = outv[a];
+        EbTrace tl, tu;
+        const float lower = eb_logits<true>(P, v - 0.5f, &tl);
+        const float upper = eb_logits<true>(P, v + 0.5f, &tu);
+        const float raw = eb_likelihood(lower, upper, form);
+        const float l = (bound > 0.f) ? fmaxf(raw, bound) : raw;
+        float g = (g_lik != nullptr ? g_lik[a] : 0.f) + gls / l;
+        if (bound > 0.f) g = lower_bound_grad(raw, bound, g);
+        float dl, du;
+        eb_likelihood_grad(lower, upper, form, &dl, &du);
+        float gv = eb_logits_backward<true>(P, v - 0.5f, tl, g * dl, gP);
+        gv += eb_logits_backward<true>(P, v + 0.5f, tu, g * du, gP);
+        // noise mode: out = x + u -> d out / d x = 1.  dequantize mode: round() has zero gradient.
+        g_x[a] = train ? (gv + (g_out != nullptr ? g_out[a] : 0.f)) : 0.f;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < EB_NP; ++k) {
+        const float s = warp_sum(gP[k]);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < EB_NP) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < EB_THREADS / 32; ++w) s += red[w][threadIdx.x];
+        s *= eb_transform_grad(threadIdx.x, Praw[threadIdx.x], P[threadIdx.x]);
+        atomicAdd(&g_params[c * EB_NP + threadIdx.x], s);
+    }
+}
+
+// _logits_cumulative on (C, L) with detached parameters
+__global__ void __launch_bounds__(EB_THREADS)
+eb_logits_kernel(const float *__restrict__ v, int64_t C, int64_t L, const float *__restrict__ params,
+                 float *__restrict__ logits) {
+    __shared__ float P[EB_NP];
+    const int64_t c = blockIdx.x;
+    if (threadIdx.x < EB_NP) P[threadIdx.x] = eb_transform(threadIdx.x, params[c * EB_NP + threadIdx.x]);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.y * blockDim.x)
+        logits[c * L + i] = eb_logits<false>(P, v[c * L + i], nullptr);
+}
+
+// aux loss: sum_c sum_{q<3} |F_c(quantiles[c][q]) - target[q]|, gradient w.r.t. quantiles only.
+// One warp per channel-triple would waste lanes; instead thread <-> (channel, q) and parameters straight from
+// global memory (the whole input is 3*C floats; this kernel exists to collapse ~35 launches into one).
+__global__ void __launch_bounds__(EB_THREADS)
+eb_aux_loss_kernel(const float *__restrict__ quantiles, int64_t C, const float *__restrict__ params,
+                   const float *__restrict__ target3, float *__restrict__ loss, float *__restrict__ g_quantiles) {
+    __shared__ float red[32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float contrib = 0.f;
+    if (i < 3 * C) {
+        const int64_t c = i / 3;
+        const int q = (int)(i - 3 * c);
+        float P[EB_NP];
+#pragma unroll
+        for (int k = 0; k < EB_NP; ++k) P[k] = eb_transform(k, params[c * EB_NP + k]);
+        const float t = quantiles[i];
+        EbTrace tr;
+        const float f = eb_logits<true>(P, t, &tr);
+        const float d = f - target3[q];
+        contrib = fabsf(d);
+        g_quantiles[i] = eb_logits_backward<false>(P, t, tr, sign_t(d), nullptr);
+    }
+    const float tot = block_sum(contrib, red);
+    if (threadIdx.x == 0) atomicAdd(loss, tot);
+}
+
+static inline int eb_splits(int64_t C, int64_t n_per_channel) {
+    // enough blocks to cover the machine a few times over, but never more than the work in a channel
+    const int64_t target_blocks = (int64_t)sm_count() * 8;
+    int64_t splits = (target_blocks + C - 1) / C;
+    const int64_t max_splits = (n_per_channel + EB_THREADS - 1) / EB_THREADS;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    return (int)splits;
+}
+
+}  // namespace mmnc
+
+using namespace mmnc;
+
+extern "C" int mmnc_eb_forward(const float *x, int64_t B, int64_t C, int64_t S, const float *params,
+                               const float *medians, int noise_mode, const float *noise, uint64_t seed,
+                               uint64_t offset, float likelihood_bound, int likelihood_form, float *out,
+                               float *lik, float *lnsum, void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && S >= 0, "eb_forward: negative dimension");
+    MMNC_REQUIRE(noise_mode >= 0 && noise_mode <= 3, "eb_forward: bad noise_mode %d", noise_mode);
+    MMNC_REQUIRE(likelihood_form == 0 || likelihood_form == 1, "eb_forward: bad likelihood_form");
+    if (B * C * S == 0) return MMNC_OK;
+    MMNC_REQUIRE(x && params && medians && out && lik, "eb_forward: null pointer");
+    MMNC_REQUIRE(noise_mode != MMNC_QUANT_NOISE_GIVEN || noise, "eb_forward: noise_mode GIVEN needs noise");
+    MMNC_REQUIRE(C <= 2147483647LL, "eb_forward: too many channels");
+    dim3 grid((unsigned)C, (unsigned)eb_splits(C, B * S));
+    eb_forward_kernel<<<grid, EB_THREADS, 0, as_stream(stream)>>>(x, B, C, S, params, medians, noise_mode, noise,
+                                                                   seed, offset, likelihood_bound, likelihood_form,
+                                                                   out, lik, lnsum);
+    return after_launch("eb_forward_kernel");
+}
+
+extern "C" int mmnc_eb_backward(const float *out, int64_t B, int64_t C, int64_t S, const float *params,
+                                const float *g_out, const float *g_lik, const float *g_lnsum,
+                                float likelihood_bound, int likelihood_form, float *g_x, float *g_params,
+                                void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && S >= 0, "eb_backward: negative dimension");
+    if (B * C * S == 0) return MMNC_OK;
+    MMNC_REQUIRE(out && params && g_x && g_params, "eb_backward: null pointer");
+    dim3 grid((unsigned)C, (unsigned)eb_splits(C, B * S));
+    eb_backward_kernel<<<grid, EB_THREADS, 0, as_stream(stream)>>>(out, B, C, S, params, g_out, g_lik, g_lnsum,
+                                                                    likelihood_bound, likelihood_form, 1, g_x,
+                                                                    g_params);
+    return after_launch("eb_backward_kernel");
+}
+
+extern "C" int mmnc_eb_logits(const float *v, int64_t C, int64_t L, const float *params, float *logits,
+                              void *stream) {
+    MMNC_REQUIRE(C >= 0 && L >= 0, "eb_logits: negative dimension");
+    if (C * L == 0) return MMNC_OK;
+    MMNC_REQUIRE(v && params && logits, "eb_logits: null pointer");
+    dim3 grid((unsigned)C, (unsigned)eb_splits(C, L));
+    eb_logits_kernel<<<grid, EB_THREADS, 0, as_stream(stream)>>>(v, C, L, params, logits);
+    return after_launch("eb_logits_kernel");
+}
+
+extern "C" int mmnc_eb_aux_loss(const float *quantiles, int64_t C, const float *params, const float *target3,
+                                float *loss, float *g_quantiles, void *stream) {
+    MMNC_REQUIRE(C >= 0, "eb_aux_loss: negative dimension");
+    if (C == 0) return MMNC_OK;
+    MMNC_REQUIRE(quantiles && params && target3 && loss && g_quantiles, "eb_aux_loss: null pointer");
+    const int64_t n = 3 * C;
+    eb_aux_loss_kernel<<<(unsigned)((n + EB_THREADS - 1) / EB_THREADS), EB_THREADS, 0, as_stream(stream)>>>(
+        quantiles, C, params, target3, loss, g_quantiles);
+    return after_launch("eb_aux_loss_kernel");
+}

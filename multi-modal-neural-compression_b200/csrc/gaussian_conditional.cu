@@ -1,0 +1,196 @@
+// K1 + K3: GaussianConditional forward / backward and the per-channel ln-likelihood reduction
+// (SURVEY.md section 8 rows a2, a5, a6).
+//
+// Replaces CompressAI's GaussianConditional.forward chain (quantise, LowerBound(scales), abs, 2 x erfc, sub,
+// LowerBound(lik): ~16 launches) plus the reference's per-group `log().sum()` (4 launches per group,
+// /root/reference/src/models/multi_task_compressor.py:288-291) with one launch per direction.
+//
+// y is (B, C, Sy), scales / lik are (B, C, Ss) with Sy == Ss or Sy == 1: the reference really produces
+// y (B,M,1,1) against scales (B,M,4,4) and relies on torch broadcasting; the
+// broadcast is a stride-0 read here and the backward sums g_y over the Ss positions with lane shuffles.
+// grid = (C, splits): a block owns one channel so the channel's sum of ln(lik) is a block reduction.
+#include "common.cuh"
+#include "hd_math.cuh"
+
+namespace mmnc {
+
+constexpr int GC_THREADS = 256;
+
+__global__ void __launch_bounds__(GC_THREADS)
+gc_forward_kernel(const float *__restrict__ y, const float *__restrict__ scales, const float *__restrict__ means,
+                  int64_t B, int64_t C, int64_t Sy, int64_t Ss, int noise_mode, const float *__restrict__ noise,
+                  uint64_t seed, uint64_t offset, float scale_bound, float lik_bound, float *__restrict__ y_hat,
+                  float *__restrict__ lik, float *__restrict__ lnsum) {
+    __shared__ float red[32];
+    const int64_t c = blockIdx.x;
+    const int64_t n = B * Ss;
+    const bool bcast = (Sy != Ss);
+    float acc = 0.f;
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
+        const int64_t b = e / Ss, s = e - b * Ss;
+        const int64_t ai = (b * C + c) * Ss + s;
+        const int64_t yi = bcast ? (b * C + c) : ai;
+        const float yv = y[yi];
+        const float m = (means != nullptr) ? means[yi] : 0.f;
+        float v;
+        if (noise_mode == MMNC_QUANT_DEQUANTIZE) v = rintf(yv - m) + m;
+        else if (noise_mode == MMNC_QUANT_NOISE_PHILOX) v = yv + philox_uniform_centered(seed, (uint64_t)yi + offset);
+        else if (noise_mode == MMNC_QUANT_NOISE_GIVEN) v = yv + noise[yi];
+        else v = yv;
+        float l = gc_likelihood(v, m, scales[ai], scale_bound);
+        if (lik_bound > 0.f) l = fmaxf(l, lik_bound);
+        lik[ai] = l;
+        if (!bcast || s == 0) y_hat[yi] = v;
+        acc += logf(l);
+    }
+    if (lnsum != nullptr) {
+        const float tot = block_sum(acc, red);
+        if (threadIdx.x == 0) atomicAdd(&lnsum[c], tot);
+    }
+}
+
+// reduce_mode: 0 = no broadcast, 1 = shuffle over groups of Ss lanes (Ss power of two <= 32), 2 = atomics
+__global__ void __launch_bounds__(GC_THREADS)
+gc_backward_kernel(const float *__restrict__ y_hat, const float *__restrict__ scales,
+                   const float *__restrict__ means, int64_t B, int64_t C, int64_t Sy, int64_t Ss,
+                   const float *__restrict__ g_yhat, const float *__restrict__ g_lik,
+                   const float *__restrict__ g_lnsum, float scale_bound, float lik_bound, int reduce_mode,
+                   float *__restrict__ g_y, float *__restrict__ g_scales) {
+    const int64_t c = blockIdx.x;
+    const int64_t n = B * Ss;
+    const bool bcast = (Sy != Ss);
+    const float gls = (g_lnsum != nullptr) ? g_lnsum[c] : 0.f;
+    for (int64_t e0 = (int64_t)blockIdx.y * blockDim.x; e0 < n; e0 += (int64_t)gridDim.y * blockDim.x) {
+        const int64_t e = e0 + threadIdx.x;
+        const bool valid = e < n;
+        float gy = 0.f;
+        int64_t yi = 0, s = 0;
+        if (valid) {
+            const int64_t b = e / Ss;
+            s = e - b * Ss;
+            const int64_t ai = (b * C + c) * Ss + s;
+            yi = bcast ? (b * C + c) : ai;
+            const float v = y_hat[yi];
+            const float m = (means != nullptr) ? means[yi] : 0.f;
+            const float sc = scales[ai];
+            const float raw = gc_likelihood(v, m, sc, scale_bound);
+            const float l = (lik_bound > 0.f) ? fmaxf(raw, lik_bound) : raw;
+            float g = (g_lik != nullptr ? g_lik[ai] : 0.f) + gls / l;
+            if (lik_bound > 0.f) g = lower_bound_grad(raw, lik_bound, g);
+            float dy, dsc;
+            gc_likelihood_grad(v, m, sc, scale_bound, &dy, &dsc);
+            gy = g * dy;
+            g_scales[ai] = lower_bound_grad(sc, scale_bound, g * dsc);
+        }
+        if (reduce_mode == 0) {
+            if (valid) g_y[yi] = gy + (g_yhat != nullptr ? g_yhat[yi] : 0.f);
+        } else if (reduce_mode == 1) {
+            for (int o = (int)Ss >> 1; o > 0; o >>= 1) gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            if (valid && s == 0) g_y[yi] = gy + (g_yhat != nullptr ? g_yhat[yi] : 0.f);
+        } else {
+            if (valid) {
+                if (s == 0 && g_yhat != nullptr) gy += g_yhat[yi];
+                atomicAdd(&g_y[yi], gy);
+            }
+        }
+    }
+}
+
+// lnsum[c] += sum_{b,s} ln lik[b,c,s]
+__global__ void __launch_bounds__(GC_THREADS)
+lnsum_forward_kernel(const float *__restrict__ lik, int64_t B, int64_t C, int64_t S, float *__restrict__ lnsum) {
+    __shared__ float red[32];
+    const int64_t c = blockIdx.x;
+    const int64_t n = B * S;
+    float acc = 0.f;
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
+        const int64_t b = e / S, s = e - b * S;
+        acc += logf(lik[(b * C + c) * S + s]);
+    }
+    const float tot = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(&lnsum[c], tot);
+}
+
+__global__ void __launch_bounds__(GC_THREADS)
+lnsum_backward_kernel(const float *__restrict__ lik, int64_t n, int64_t C, int64_t S,
+                      const float *__restrict__ g_lnsum, float *__restrict__ g_lik) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = (i / S) % C;
+        g_lik[i] = g_lnsum[c] / lik[i];
+    }
+}
+
+static inline int gc_splits(int64_t C, int64_t n_per_channel) {
+    const int64_t target_blocks = (int64_t)sm_count() * 8;
+    int64_t splits = (target_blocks + C - 1) / C;
+    const int64_t max_splits = (n_per_channel + GC_THREADS - 1) / GC_THREADS;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    return (int)splits;
+}
+
+}  // namespace mmnc
+
+using namespace mmnc;
+
+extern "C" int mmnc_gc_forward(const float *y, const float *scales, const float *means, int64_t B, int64_t C,
+                               int64_t Sy, int64_t Ss, int noise_mode, const float *noise, uint64_t seed,
+                               uint64_t offset, float scale_bound, float likelihood_bound, float *y_hat,
+                               float *lik, float *lnsum, void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && Sy >= 0 && Ss >= 0, "gc_forward: negative dimension");
+    MMNC_REQUIRE(Sy == Ss || Sy == 1, "gc_forward: y spatial size must equal the scales' or be 1 (got %lld vs %lld)",
+                 (long long)Sy, (long long)Ss);
+    MMNC_REQUIRE(noise_mode >= 0 && noise_mode <= 3, "gc_forward: bad noise_mode %d", noise_mode);
+    if (B * C * Ss == 0) return MMNC_OK;
+    MMNC_REQUIRE(y && scales && y_hat && lik, "gc_forward: null pointer");
+    MMNC_REQUIRE(noise_mode != MMNC_QUANT_NOISE_GIVEN || noise, "gc_forward: noise_mode GIVEN needs noise");
+    dim3 grid((unsigned)C, (unsigned)gc_splits(C, B * Ss));
+    gc_forward_kernel<<<grid, GC_THREADS, 0, as_stream(stream)>>>(y, scales, means, B, C, Sy, Ss, noise_mode,
+                                                                   noise, seed, offset, scale_bound,
+                                                                   likelihood_bound, y_hat, lik, lnsum);
+    return after_launch("gc_forward_kernel");
+}
+
+extern "C" int mmnc_gc_backward(const float *y_hat, const float *scales, const float *means, int64_t B, int64_t C,
+                                int64_t Sy, int64_t Ss, const float *g_yhat, const float *g_lik,
+                                const float *g_lnsum, float scale_bound, float likelihood_bound, float *g_y,
+                                float *g_scales, void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && Sy >= 0 && Ss >= 0, "gc_backward: negative dimension");
+    MMNC_REQUIRE(Sy == Ss || Sy == 1, "gc_backward: unsupported broadcast");
+    if (B * C * Ss == 0) return MMNC_OK;
+    MMNC_REQUIRE(y_hat && scales && g_y && g_scales, "gc_backward: null pointer");
+    int reduce_mode = 0;
+    if (Sy != Ss) {
+        const bool pow2 = (Ss & (Ss - 1)) == 0;
+        reduce_mode = (pow2 && Ss <= 32) ? 1 : 2;
+        if (reduce_mode == 2) MMNC_CUDA(cudaMemsetAsync(g_y, 0, sizeof(float) * (size_t)(B * C * Sy), as_stream(stream)));
+    }
+    dim3 grid((unsigned)C, (unsigned)gc_splits(C, B * Ss));
+    gc_backward_kernel<<<grid, GC_THREADS, 0, as_stream(stream)>>>(y_hat, scales, means, B, C, Sy, Ss, g_yhat, g_lik,
+                                                                    g_lnsum, scale_bound, likelihood_bound,
+                                                                    reduce_mode, g_y, g_scales);
+    return after_launch("gc_backward_kernel");
+}
+
+extern "C" int mmnc_lnsum_forward(const float *lik, int64_t B, int64_t C, int64_t S, float *lnsum, void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && S >= 0, "lnsum_forward: negative dimension");
+    if (B * C * S == 0) return MMNC_OK;
+    MMNC_REQUIRE(lik && lnsum, "lnsum_forward: null pointer");
+    dim3 grid((unsigned)C, (unsigned)gc_splits(C, B * S));
+    lnsum_forward_kernel<<<grid, GC_THREADS, 0, as_stream(stream)>>>(lik, B, C, S, lnsum);
+    return after_launch("lnsum_forward_kernel");
+}
+
+extern "C" int mmnc_lnsum_backward(const float *lik, int64_t B, int64_t C, int64_t S, const float *g_lnsum,
+                                   float *g_lik, void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && S >= 0, "lnsum_backward: negative dimension");
+    const int64_t n = B * C * S;
+    if (n == 0) return MMNC_OK;
+    MMNC_REQUIRE(lik && g_lnsum && g_lik, "lnsum_backward: null pointer");
+    int64_t blocks = (n + GC_THREADS - 1) / GC_THREADS;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    lnsum_backward_kernel<<<(unsigned)blocks, GC_THREADS, 0, as_stream(stream)>>>(lik, n, C, S, g_lnsum, g_lik);
+    return after_launch("lnsum_backward_kernel");
+}

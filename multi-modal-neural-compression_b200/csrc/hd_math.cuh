@@ -1,0 +1,297 @@
+// Per-element arithmetic of the rate path, written once as host+device inline functions.
+// The CUDA kernels call these; tests/hostcheck compiles the same header with g++ to check the logic against
+// the oracle without a GPU (test infrastructure only — the shipped library exports GPU entry points only).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MMNC_HD __host__ __device__ __forceinline__
+#else
+#define MMNC_HD inline
+#endif
+
+namespace mmnc {
+
+// ---------------------------------------------------------------------------------------------- scalars
+MMNC_HD float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // F.softplus(beta=1, threshold=20)
+MMNC_HD float sigmoid_t(float x) { return 1.f / (1.f + expf(-x)); }
+MMNC_HD float sign_t(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// Philox4x32-10 keyed by a 64-bit seed, counter = 64-bit element index.  Returns U[-0.5, 0.5).
+MMNC_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+MMNC_HD float philox_uniform_centered(uint64_t seed, uint64_t index) {
+    uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return (float)(c0 >> 8) * (1.0f / 16777216.0f) - 0.5f;  // 24-bit mantissa, [0,1) - 0.5
+}
+
+// ---------------------------------------------------------------------------------------------- EB (A.3)
+// Packed per-channel parameter layout (58 floats), see include/mmnc_b200.h.
+constexpr int EB_NP = 58;
+MMNC_HD bool eb_is_matrix(int k) { return k < 3 || (k >= 9 && k < 18) || (k >= 24 && k < 33) || (k >= 39 && k < 48) || (k >= 54 && k < 57); }
+MMNC_HD bool eb_is_factor(int k) { return (k >= 6 && k < 9) || (k >= 21 && k < 24) || (k >= 36 && k < 39) || (k >= 51 && k < 54); }
+// raw -> what the MLP consumes: softplus(matrix), bias, tanh(factor)
+MMNC_HD float eb_transform(int k, float raw) { return eb_is_matrix(k) ? softplus_t(raw) : (eb_is_factor(k) ? tanhf(raw) : raw); }
+// d transformed / d raw, given raw and transformed values
+MMNC_HD float eb_transform_grad(int k, float raw, float tr) {
+    return eb_is_matrix(k) ? sigmoid_t(raw) : (eb_is_factor(k) ? (1.f - tr * tr) : 1.f);
+}
+
+// activations kept for the backward pass of one logits evaluation
+struct EbTrace {
+    float h[4][3];   // inputs of layers 1..4 (h[0] = output of layer 0's gate, ...)
+    float th[4][3];  // tanh(pre-activation) of layers 0..3
+};
+
+template <bool kTrace>
+MMNC_HD float eb_logits(const float *P, float t, EbTrace *tr) {
+    float h[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = P[i] * t + P[3 + i];
+        const float ta = tanhf(a);
+        h[i] = a + P[6 + i] * ta;
+        if (kTrace) { tr->th[0][i] = ta; tr->h[0][i] = h[i]; }
+    }
+#pragma unroll
+    for (int l = 1; l < 4; ++l) {
+        const int base = 9 + (l - 1) * 15;
+        float n[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float a = P[base + 3 * i] * h[0];
+            a += P[base + 3 * i + 1] * h[1];
+            a += P[base + 3 * i + 2] * h[2];
+            a += P[base + 9 + i];
+            const float ta = tanhf(a);
+            n[i] = a + P[base + 12 + i] * ta;
+            if (kTrace) { tr->th[l][i] = ta; }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { h[i] = n[i]; if (kTrace) tr->h[l][i] = n[i]; }
+    }
+    float f = P[54] * h[0];
+    f += P[55] * h[1];
+    f += P[56] * h[2];
+    f += P[57];
+    return f;
+}
+
+// Back-propagates dF through one traced evaluation.  Accumulates gradients w.r.t. the TRANSFORMED parameters
+// into gP (58, may be null when parameters are detached) and returns dF/dt * dF.
+template <bool kParamGrads>
+MMNC_HD float eb_logits_backward(const float *P, float t, const EbTrace &tr, float dF, float *gP) {
+    float gh[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        gh[j] = dF * P[54 + j];
+        if (kParamGrads) gP[54 + j] += dF * tr.h[3][j];
+    }
+    if (kParamGrads) gP[57] += dF;
+#pragma unroll
+    for (int l = 3; l >= 1; --l) {
+        const int base = 9 + (l - 1) * 15;
+        float ga[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float ta = tr.th[l][i];
+            ga[i] = gh[i] * (1.f + P[base + 12 + i] * (1.f - ta * ta));
+            if (kParamGrads) {
+                gP[base + 12 + i] += gh[i] * ta;
+                gP[base + 9 + i] += ga[i];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) gP[base + 3 * i + j] += ga[i] * tr.h[l - 1][j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            gh[j] = ga[0] * P[base + j] + ga[1] * P[base + 3 + j] + ga[2] * P[base + 6 + j];
+    }
+    float dt = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float ta = tr.th[0][i];
+        const float ga = gh[i] * (1.f + P[6 + i] * (1.f - ta * ta));
+        if (kParamGrads) {
+            gP[6 + i] += gh[i] * ta;
+            gP[3 + i] += ga;
+            gP[i] += ga * t;
+        }
+        dt += ga * P[i];
+    }
+    return dt;
+}
+
+// likelihood from the two logits (before the floor); also the partial derivatives w.r.t. (lower, upper)
+MMNC_HD float eb_likelihood(float lower, float upper, int form) {
+    if (form == 0) {
+        const float s = -sign_t(lower + upper);
+        return fabsf(sigmoid_t(s * upper) - sigmoid_t(s * lower));
+    }
+    return sigmoid_t(upper) - sigmoid_t(lower);
+}
+MMNC_HD void eb_likelihood_grad(float lower, float upper, int form, float *d_lower, float *d_upper) {
+    if (form == 0) {
+        const float s = -sign_t(lower + upper);
+        const float su = sigmoid_t(s * upper), sl = sigmoid_t(s * lower);
+        const float sg = sign_t(su - sl);
+        *d_upper = sg * s * su * (1.f - su);
+        *d_lower = -sg * s * sl * (1.f - sl);
+    } else {
+        const float su = sigmoid_t(upper), sl = sigmoid_t(lower);
+        *d_upper = su * (1.f - su);
+        *d_lower = -sl * (1.f - sl);
+    }
+}
+
+// LowerBound custom gradient (A.2): pass when x >= bound or the gradient is negative
+MMNC_HD float lower_bound_grad(float x, float bound, float g) { return (x >= bound || g < 0.f) ? g : 0.f; }
+
+// ---------------------------------------------------------------------------------------------- GC (A.4)
+constexpr float GC_CONST = -0.70710678118654752440f;      // -(2 ** -0.5)
+constexpr float INV_SQRT_2PI = 0.39894228040143267794f;
+
+MMNC_HD float gc_std_cumulative(float t) { return 0.5f * erfcf(GC_CONST * t); }
+
+MMNC_HD float gc_likelihood(float y_hat, float mean, float scale, float scale_bound) {
+    const float sc = fmaxf(scale, scale_bound);
+    const float v = fabsf(y_hat - mean);
+    const float upper = gc_std_cumulative((0.5f - v) / sc);
+    const float lower = gc_std_cumulative((-0.5f - v) / sc);
+    return upper - lower;
+}
+// d lik / d y_hat and d lik / d (bounded scale)
+MMNC_HD void gc_likelihood_grad(float y_hat, float mean, float scale, float scale_bound, float *d_y, float *d_sc) {
+    const float sc = fmaxf(scale, scale_bound);
+    const float d = y_hat - mean;
+    const float v = fabsf(d);
+    const float tu = (0.5f - v) / sc, tl = (-0.5f - v) / sc;
+    const float pu = INV_SQRT_2PI * expf(-0.5f * tu * tu), pl = INV_SQRT_2PI * expf(-0.5f * tl * tl);
+    *d_y = sign_t(d) * (pl - pu) / sc;
+    *d_sc = (tl * pl - tu * pu) / sc;
+}
+
+// ---------------------------------------------------------------------------------------------- indexes (A.4)
+// idx = (n-1) - #{ t in table[0..n-2] : s <= t } with s = max(scale, bound); NaN -> n-1.
+MMNC_HD int gc_scale_index(float scale, float bound, const float *table, int n) {
+    const float s = fmaxf(scale, bound);
+    if (!(s == s)) return n - 1;
+    // first k in [0, n-1) with table[k] >= s  (table ascending)
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (table[mid] >= s) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------- rANS (A.7)
+constexpr uint64_t RANS_L = 1ull << 31;
+constexpr int RANS_PRECISION = 16;
+constexpr int RANS_BYPASS_BITS = 4;
+constexpr int RANS_BYPASS_MAX = 15;
+
+struct RansEnc {
+    uint64_t x;
+    uint32_t *ptr;  // write pointer, moves backwards
+    MMNC_HD void init(uint32_t *end) { x = RANS_L; ptr = end; }
+    MMNC_HD void put(uint32_t start, uint32_t freq) {
+        const uint64_t x_max = ((RANS_L >> RANS_PRECISION) << 32) * freq;
+        if (x >= x_max) { *--ptr = (uint32_t)x; x >>= 32; }
+        x = ((x / freq) << RANS_PRECISION) + (x % freq) + start;
+    }
+    MMNC_HD void put_bits(uint32_t val) {
+        const uint64_t x_max = ((RANS_L >> 16) << 32) * (uint64_t)(1u << (16 - RANS_BYPASS_BITS));
+        if (x >= x_max) { *--ptr = (uint32_t)x; x >>= 32; }
+        x = (x << RANS_BYPASS_BITS) | val;
+    }
+    MMNC_HD void flush() { ptr -= 2; ptr[0] = (uint32_t)x; ptr[1] = (uint32_t)(x >> 32); }
+};
+
+// number of 4-bit groups needed for raw (0 for raw == 0)
+MMNC_HD int rans_nibbles(uint32_t raw) {
+    int n = 0;
+    while (n < 8 && (raw >> (n * RANS_BYPASS_BITS)) != 0) ++n;
+    return n;
+}
+
+// Encodes the escape tail of one symbol (count digits + nibbles) — called BEFORE put() of the symbol itself
+// because the coder consumes pushes in reverse order.
+MMNC_HD void rans_put_escape_reversed(RansEnc &e, uint32_t raw) {
+    const int nb = rans_nibbles(raw);
+    for (int j = nb - 1; j >= 0; --j) e.put_bits((raw >> (j * RANS_BYPASS_BITS)) & RANS_BYPASS_MAX);
+    // count digits were pushed as: 15, 15, ..., rest ; reversed: rest first
+    // (nb <= 8 < 15, so there is exactly one digit; kept general)
+    int full = nb / RANS_BYPASS_MAX, rest = nb - full * RANS_BYPASS_MAX;
+    e.put_bits((uint32_t)rest);
+    for (int k = 0; k < full; ++k) e.put_bits(RANS_BYPASS_MAX);
+}
+
+// symbol -> (cdf slot, raw escape payload).  Returns the slot; *raw is meaningful only when slot == max_value.
+MMNC_HD int rans_map_symbol(int32_t symbol, int32_t offset, int32_t max_value, uint32_t *raw) {
+    int32_t value = symbol - offset;
+    *raw = 0;
+    if (value < 0) { *raw = (uint32_t)(-2 * value - 1); value = max_value; }
+    else if (value >= max_value) { *raw = (uint32_t)(2 * (value - max_value)); value = max_value; }
+    return value;
+}
+
+struct RansDec {
+    uint64_t x;
+    const uint8_t *p;    // read cursor (bytes; streams need not be 4-byte aligned)
+    const uint8_t *end;
+    bool overrun;
+    MMNC_HD uint32_t word() {
+        if (p + 4 > end) { overrun = true; return 0; }
+        const uint32_t w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        p += 4;
+        return w;
+    }
+    MMNC_HD void init(const uint8_t *begin, const uint8_t *end_) {
+        p = begin; end = end_; overrun = false;
+        const uint64_t lo = word();
+        const uint64_t hi = word();
+        x = lo | (hi << 32);
+    }
+    MMNC_HD uint32_t peek() const { return (uint32_t)(x & 0xFFFFu); }
+    MMNC_HD void advance(uint32_t start, uint32_t freq) {
+        x = (uint64_t)freq * (x >> RANS_PRECISION) + (x & 0xFFFFu) - start;
+        if (x < RANS_L) x = (x << 32) | word();
+    }
+    MMNC_HD uint32_t get_bits() {
+        const uint32_t val = (uint32_t)(x & RANS_BYPASS_MAX);
+        x >>= RANS_BYPASS_BITS;
+        if (x < RANS_L) x = (x << 32) | word();
+        return val;
+    }
+    MMNC_HD int32_t get_escape(int32_t max_value) {
+        int32_t val = (int32_t)get_bits();
+        int32_t nb = val;
+        while (val == RANS_BYPASS_MAX && !overrun) { val = (int32_t)get_bits(); nb += val; }
+        uint32_t raw = 0;
+        for (int j = 0; j < nb && j < 8; ++j) raw |= get_bits() << (j * RANS_BYPASS_BITS);
+        int32_t value = (int32_t)(raw >> 1);
+        return (raw & 1u) ? (-value - 1) : (value + max_value);
+    }
+};
+
+// s = (first position in cdf[0..len) with value > cum) - 1, by binary search (cdf strictly increasing)
+MMNC_HD int rans_find_slot(const int32_t *cdf, int len, uint32_t cum) {
+    int lo = 0, hi = len;  // first index with cdf > cum
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((uint32_t)cdf[mid] > cum) hi = mid; else lo = mid + 1;
+    }
+    return lo - 1;
+}
+
+}  // namespace mmnc
