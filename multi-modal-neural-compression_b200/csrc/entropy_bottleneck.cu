@@ -45,7 +45,7 @@ eb_forward_kernel(const float *__restrict__ x, int64_t B, int64_t C, int64_t S, 
         const float lower = eb_logits<false>(P, v - 0.5f, nullptr);
         const float upper = eb_logits<false>(P, v + 0.5f, nullptr);
         float l = eb_likelihood(lower, upper, form);
-        if (bound > 0.f) l = fmaxf(l, bound);
+        if (bound > 0.f) l = max_nan(l, bound);
         out[a] = v;
         lik[a] = l;
         acc += logf(l);
@@ -83,7 +83,7 @@ eb_backward_kernel(const float *__restrict__ outv, int64_t B, int64_t C, int64_t
         const float lower = eb_logits<true>(P, v - 0.5f, &tl);
         const float upper = eb_logits<true>(P, v + 0.5f, &tu);
         const float raw = eb_likelihood(lower, upper, form);
-        const float l = (bound > 0.f) ? fmaxf(raw, bound) : raw;
+        const float l = (bound > 0.f) ? max_nan(raw, bound) : raw;
         float g = (g_lik != nullptr ? g_lik[a] : 0.f) + gls / l;
         if (bound > 0.f) g = lower_bound_grad(raw, bound, g);
         float dl, du;

@@ -38,7 +38,7 @@ gc_forward_kernel(const float *__restrict__ y, const float *__restrict__ scales,
         else if (noise_mode == MMNC_QUANT_NOISE_GIVEN) v = yv + noise[yi];
         else v = yv;
         float l = gc_likelihood(v, m, scales[ai], scale_bound);
-        if (lik_bound > 0.f) l = fmaxf(l, lik_bound);
+        if (lik_bound > 0.f) l = max_nan(l, lik_bound);
         lik[ai] = l;
         if (!bcast || s == 0) y_hat[yi] = v;
         acc += logf(l);
@@ -74,7 +74,7 @@ gc_backward_kernel(const float *__restrict__ y_hat, const float *__restrict__ sc
             const float m = (means != nullptr) ? means[yi] : 0.f;
             const float sc = scales[ai];
             const float raw = gc_likelihood(v, m, sc, scale_bound);
-            const float l = (lik_bound > 0.f) ? fmaxf(raw, lik_bound) : raw;
+            const float l = (lik_bound > 0.f) ? max_nan(raw, lik_bound) : raw;
             float g = (g_lik != nullptr ? g_lik[ai] : 0.f) + gls / l;
             if (lik_bound > 0.f) g = lower_bound_grad(raw, lik_bound, g);
             float dy, dsc;

@@ -17,6 +17,8 @@ namespace mmnc {
 MMNC_HD float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // F.softplus(beta=1, threshold=20)
 MMNC_HD float sigmoid_t(float x) { return 1.f / (1.f + expf(-x)); }
 MMNC_HD float sign_t(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+// torch.max(x, bound): unlike fmaxf it propagates a NaN in x (LowerBound must not hide a diverged value)
+MMNC_HD float max_nan(float x, float bound) { return (x != x) ? x : fmaxf(x, bound); }
 
 // Philox4x32-10 keyed by a 64-bit seed, counter = 64-bit element index.  Returns U[-0.5, 0.5).
 MMNC_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
@@ -163,7 +165,7 @@ constexpr float INV_SQRT_2PI = 0.39894228040143267794f;
 MMNC_HD float gc_std_cumulative(float t) { return 0.5f * erfcf(GC_CONST * t); }
 
 MMNC_HD float gc_likelihood(float y_hat, float mean, float scale, float scale_bound) {
-    const float sc = fmaxf(scale, scale_bound);
+    const float sc = max_nan(scale, scale_bound);
     const float v = fabsf(y_hat - mean);
     const float upper = gc_std_cumulative((0.5f - v) / sc);
     const float lower = gc_std_cumulative((-0.5f - v) / sc);
@@ -171,7 +173,7 @@ MMNC_HD float gc_likelihood(float y_hat, float mean, float scale, float scale_bo
 }
 // d lik / d y_hat and d lik / d (bounded scale)
 MMNC_HD void gc_likelihood_grad(float y_hat, float mean, float scale, float scale_bound, float *d_y, float *d_sc) {
-    const float sc = fmaxf(scale, scale_bound);
+    const float sc = max_nan(scale, scale_bound);
     const float d = y_hat - mean;
     const float v = fabsf(d);
     const float tu = (0.5f - v) / sc, tl = (-0.5f - v) / sc;
@@ -183,8 +185,8 @@ MMNC_HD void gc_likelihood_grad(float y_hat, float mean, float scale, float scal
 // ---------------------------------------------------------------------------------------------- indexes (A.4)
 // idx = (n-1) - #{ t in table[0..n-2] : s <= t } with s = max(scale, bound); NaN -> n-1.
 MMNC_HD int gc_scale_index(float scale, float bound, const float *table, int n) {
-    const float s = fmaxf(scale, bound);
-    if (!(s == s)) return n - 1;
+    const float s = max_nan(scale, bound);
+    if (s != s) return n - 1;  // every comparison with NaN is false -> nothing is subtracted
     // first k in [0, n-1) with table[k] >= s  (table ascending)
     int lo = 0, hi = n - 1;
     while (lo < hi) {

@@ -125,7 +125,7 @@ rd_epilogue_kernel(const float *__restrict__ lnsum_y, int64_t M, const float *__
 __global__ void __launch_bounds__(D_THREADS)
 nonneg_forward_kernel(const float *__restrict__ p, int64_t n, float bound, float pedestal, float *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = fmaxf(p[i], bound);
+        const float v = max_nan(p[i], bound);
         out[i] = v * v - pedestal;
     }
 }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(D_THREADS)
 nonneg_backward_kernel(const float *__restrict__ p, const float *__restrict__ g_out, int64_t n, float bound,
                        float *__restrict__ g_p) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = fmaxf(p[i], bound);
+        const float v = max_nan(p[i], bound);
         const float g = 2.f * v * g_out[i];  // gradient arriving at LowerBound's output
         g_p[i] = lower_bound_grad(p[i], bound, g);
     }

@@ -75,6 +75,16 @@ class EntropyModel(nn.Module):
         self.register_buffer("_quantized_cdf", torch.IntTensor())
         self.register_buffer("_cdf_length", torch.IntTensor())
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # CompressAI resizes these registered buffers on load (update_registered_buffers); same here so that
+        # state dicts saved after update() load into a freshly built module.
+        for name in ("_offset", "_quantized_cdf", "_cdf_length", "scale_table"):
+            key = prefix + name
+            buf = getattr(self, name, None)
+            if key in state_dict and isinstance(buf, torch.Tensor) and buf.shape != state_dict[key].shape:
+                setattr(self, name, torch.empty(state_dict[key].shape, dtype=buf.dtype, device=buf.device))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def _lik_bound(self) -> float:
         return self.likelihood_lower_bound.value() if self.use_likelihood_bound else 0.0
 
@@ -95,7 +105,7 @@ class EntropyModel(nn.Module):
         if mode not in ("noise", "dequantize", "symbols"):
             raise ValueError(f'Invalid quantization mode: "{mode}"')
         if mode == "noise":
-            return inputs + (ops.quantize_noise(inputs.detach()) - inputs.detach())  # d/dx = 1, like x + noise
+            return ops._AddNoise.apply(inputs, None, None, 0)  # d/dx = 1, like x + noise
         if mode == "dequantize":
             return ops._StraightRound.apply(inputs, means)
         return ops.quantize_symbols(inputs.detach(), None if means is None else means.detach())

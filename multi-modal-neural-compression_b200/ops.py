@@ -277,12 +277,24 @@ def gaussian_conditional_forward(y: Tensor, scales: Tensor, means: Optional[Tens
     if mode == QUANT_DEQUANTIZE:
         y_hat = _StraightRound.apply(y, means)
     else:
-        y_hat = y + (quantize_noise(y.detach(), noise=noise, seed=seed, offset=offset) - y.detach())
+        y_hat = _AddNoise.apply(y, noise, seed, offset)
     yb, sb = torch.broadcast_tensors(y_hat, scales)
     mb = None if means is None else means.expand_as(yb)
     _, lik, lnsum = _GaussianConditionalFn.apply(yb.contiguous(), sb.contiguous(), mb, QUANT_IDENTITY, None, 0, 0,
                                                  float(scale_bound), float(lik_bound))
     return y_hat, lik, lnsum
+
+
+class _AddNoise(torch.autograd.Function):
+    """x + U(-1/2, 1/2) (or + given noise) with d/dx = 1."""
+
+    @staticmethod
+    def forward(ctx, x, noise, seed, offset):
+        return quantize_noise(x, noise=noise, seed=seed, offset=offset)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None, None
 
 
 class _StraightRound(torch.autograd.Function):

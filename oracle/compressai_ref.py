@@ -121,6 +121,16 @@ class EntropyModel(nn.Module):
         # "faithful" = five .tolist() marshals per image like CompressAI; "lean" = ndarray views
         self.marshalling = "faithful"
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # CompressAI resizes these registered buffers on load (update_registered_buffers); same here so that
+        # state dicts saved after update() load into a freshly built module.
+        for name in ("_offset", "_quantized_cdf", "_cdf_length", "scale_table"):
+            key = prefix + name
+            buf = getattr(self, name, None)
+            if key in state_dict and isinstance(buf, torch.Tensor) and buf.shape != state_dict[key].shape:
+                setattr(self, name, torch.empty(state_dict[key].shape, dtype=buf.dtype, device=buf.device))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def quantize(self, inputs: Tensor, mode: str, means: Optional[Tensor] = None) -> Tensor:
         if mode not in ("noise", "dequantize", "symbols"):
             raise ValueError(f'Invalid quantization mode: "{mode}"')

@@ -23,7 +23,7 @@ void hc_eb_forward(const float *v, int C, int L, const float *params, float boun
             const float t = v[c * L + i];
             const float lo = eb_logits<false>(P, t - 0.5f, nullptr), up = eb_logits<false>(P, t + 0.5f, nullptr);
             float l = eb_likelihood(lo, up, form);
-            if (bound > 0.f) l = fmaxf(l, bound);
+            if (bound > 0.f) l = max_nan(l, bound);
             lik[c * L + i] = l;
             if (lower_out) lower_out[c * L + i] = lo;
             if (upper_out) upper_out[c * L + i] = up;
@@ -59,7 +59,7 @@ void hc_gc_forward(const float *y_hat, const float *scales, int64_t n, float sca
                    float *lik, float *d_y, float *d_sc) {
     for (int64_t i = 0; i < n; ++i) {
         float l = gc_likelihood(y_hat[i], 0.f, scales[i], scale_bound);
-        if (lik_bound > 0.f) l = fmaxf(l, lik_bound);
+        if (lik_bound > 0.f) l = max_nan(l, lik_bound);
         lik[i] = l;
         gc_likelihood_grad(y_hat[i], 0.f, scales[i], scale_bound, &d_y[i], &d_sc[i]);
     }

@@ -1,0 +1,606 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (via the package's ops), against the oracle on
+identical seeded inputs.  Bit-exact for symbols / indexes / tables / byte strings; tiered 1e-5 relative for
+likelihoods (helpers.assert_likelihood_close); stated tolerances for GDN.  Run with `-m gpu` on a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mmnc_b200 as mm
+from helpers import assert_likelihood_close, eb_double, load_golden, perturb_eb_
+from oracle import compressai_ref as R
+from oracle import native
+from oracle import reference_models as orm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pair_eb(C, perturbed=True, form="sign", seed=7):
+    ref = R.EntropyBottleneck(C, likelihood_form=form)
+    if perturbed:
+        perturb_eb_(ref, seed)
+    ours = mm.EntropyBottleneck(C, likelihood_form=form)
+    ours.load_state_dict(ref.state_dict())
+    return ours, ref
+
+
+@pytest.fixture(scope="module")
+def gc_pair():
+    ours, ref = mm.GaussianConditional(None), R.GaussianConditional(None)
+    ours.update_scale_table(mm.get_scale_table())
+    ref.update_scale_table(R.get_scale_table())
+    return ours.to(DEV), ref
+
+
+# ------------------------------------------------------------------------------------------------ a2
+def test_quantize_family_bit_exact():
+    torch.manual_seed(0)
+    x = torch.randn(3, 5, 4, 6) * 9
+    x[0, 0, 0, :6] = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, -2.5])  # round-half-to-even cases
+    med = torch.randn(5, 1, 1)
+    em, er = mm.EntropyModel(), R.EntropyModel()
+    xd, md = x.to(DEV), med.to(DEV)
+    assert torch.equal(em.quantize(xd, "dequantize", md.reshape(1, 5, 1, 1)).cpu(), er.quantize(x, "dequantize", med))
+    assert torch.equal(em.quantize(xd, "symbols", md.reshape(1, 5, 1, 1)).cpu(), er.quantize(x, "symbols", med))
+    assert torch.equal(em.quantize(xd, "dequantize").cpu(), torch.round(x))
+    full = torch.randn_like(x)
+    assert torch.equal(em.quantize(xd, "symbols", full.to(DEV)).cpu(), er.quantize(x, "symbols", full))
+    sym = er.quantize(x, "symbols", med)
+    assert torch.equal(em.dequantize(sym.to(DEV), md.reshape(1, 5, 1, 1)).cpu(), er.dequantize(sym, med.expand(3, 5, 1, 1)))
+    n = em.quantize(xd, "noise").cpu() - x
+    assert n.min() >= -0.5001 and n.max() <= 0.5001 and abs(n.mean()) < 0.05 and abs(n.var() - 1 / 12) < 0.02
+    noise = torch.rand_like(x) - 0.5
+    assert torch.equal(mm.ops.quantize_noise(xd, noise=noise.to(DEV)).cpu(), x + noise)
+    with pytest.raises(ValueError):
+        em.quantize(xd, "nearest")
+
+
+# ------------------------------------------------------------------------------------------------ a3
+@pytest.mark.parametrize("shape", [(64, 30, 1, 1), (5, 6, 3, 2), (2, 33, 4, 4), (7, 1, 1, 1), (3, 9)])
+@pytest.mark.parametrize("perturbed", [False, True])
+def test_eb_forward_eval_and_train(shape, perturbed):
+    torch.manual_seed(1)
+    C = shape[1]
+    ours, ref = _pair_eb(C, perturbed)
+    ours.to(DEV)
+    z = torch.randn(*shape) * 5
+    z.view(-1)[:2] = torch.tensor([70.0, -70.0])
+    refd = eb_double(ref)
+    # eval: dequantize with medians
+    ours.eval(), ref.eval(), refd.eval()
+    out, lik = ours(z.to(DEV))
+    out_r, lik_r = ref(z)
+    _, lik_d = refd(z.double())
+    assert torch.equal(out.cpu(), out_r)
+    assert_likelihood_close(lik, lik_r, want64=lik_d, what="EB eval")
+    assert torch.allclose(ours.last_log_likelihood_sums.cpu().double(),
+                          torch.log(lik_r.double()).transpose(0, 1).reshape(C, -1).sum(1), rtol=2e-5, atol=1e-4)
+    # train with injected noise
+    ours.train(), ref.train(), refd.train()
+    noise = torch.rand(*shape) - 0.5
+    out, lik = ours(z.to(DEV), noise=noise.to(DEV))
+    out_r, lik_r = ref(z, noise=noise)
+    _, lik_d = refd(z.double(), noise=noise.double())
+    assert torch.equal(out.cpu(), out_r)
+    assert_likelihood_close(lik, lik_r, want64=lik_d, what="EB train")
+
+
+def test_eb_golden_fixture():
+    fx = load_golden()
+    ours = mm.EntropyBottleneck(6)
+    ours.load_state_dict({k: torch.from_numpy(v) for k, v in fx["eb_state"].item().items()})
+    ours.to(DEV).eval()
+    z = torch.from_numpy(fx["eb_z"]).to(DEV)
+    out, lik = ours(z)
+    assert np.array_equal(out.cpu().numpy(), fx["eb_eval_out"])
+    assert_likelihood_close(lik, torch.from_numpy(fx["eb_eval_lik"]), rtol=2e-5, what="EB golden eval")
+    assert [s for s in ours.compress(z)] == [w.tobytes() for w in fx["eb_strings"]]
+    ours.train()
+    out, lik = ours(z, noise=torch.from_numpy(fx["eb_noise"]).to(DEV))
+    assert np.array_equal(out.cpu().numpy(), fx["eb_train_out"])
+    assert_likelihood_close(lik, torch.from_numpy(fx["eb_train_lik"]), rtol=2e-5, what="EB golden train")
+    assert abs(ours.loss().item() - float(fx["eb_aux_loss"])) <= 1e-5 * abs(float(fx["eb_aux_loss"]))
+
+
+def test_eb_plain_form_and_philox_noise():
+    torch.manual_seed(2)
+    ours, ref = _pair_eb(8, True, form="plain")
+    ours.to(DEV).eval(), ref.eval()
+    z = torch.randn(16, 8, 2, 2) * 3
+    _, lik = ours(z.to(DEV))
+    _, lik_r = ref(z)
+    assert_likelihood_close(lik, lik_r, rtol=1e-4, tail_rtol=5e-2, floor_atol=1e-8, what="EB plain")
+    ours.train()
+    torch.manual_seed(5)
+    a, _ = ours(z.to(DEV))
+    torch.manual_seed(5)
+    b, _ = ours(z.to(DEV))
+    assert torch.equal(a, b), "same torch seed -> same Philox noise"
+    d = (a.cpu() - z)
+    assert d.abs().max() <= 0.5 and d.std() > 0.2
+
+
+def test_eb_backward_matches_autograd():
+    torch.manual_seed(3)
+    C = 6
+    ours, ref = _pair_eb(C, True)
+    refd = eb_double(ref).train()
+    ours.to(DEV).train()
+    z = (torch.randn(9, C, 2, 3) * 4)
+    noise = torch.rand_like(z) - 0.5
+    g_lik, g_out = torch.randn_like(z), torch.randn_like(z)
+    zd = z.to(DEV).requires_grad_(True)
+    out, lik = ours(zd, noise=noise.to(DEV))
+    lnsum = ours.last_log_likelihood_sums
+    w = torch.randn(C)
+    ((lik * g_lik.to(DEV)).sum() + (out * g_out.to(DEV)).sum() + (lnsum * w.to(DEV)).sum()).backward()
+    z64 = z.double().requires_grad_(True)
+    out_r, lik_r = refd(z64, noise=noise.double())
+    ln_r = torch.log(lik_r).transpose(0, 1).reshape(C, -1).sum(1)
+    ((lik_r * g_lik.double()).sum() + (out_r * g_out.double()).sum() + (ln_r * w.double()).sum()).backward()
+    assert torch.allclose(zd.grad.cpu().double(), z64.grad, rtol=2e-3, atol=1e-5)
+    for name, p in ours.named_parameters():
+        if name == "quantiles":
+            continue
+        want = dict(refd.named_parameters())[name].grad
+        assert torch.allclose(p.grad.cpu().double(), want, rtol=2e-3, atol=2e-4), name
+
+
+def test_eb_aux_loss_and_gradient():
+    ours, ref = _pair_eb(12, True)
+    ours.to(DEV)
+    l, lr = ours.loss(), ref.loss()
+    assert abs(l.item() - lr.item()) <= 1e-5 * abs(lr.item())
+    l.backward(), lr.backward()
+    assert torch.allclose(ours.quantiles.grad.cpu(), ref.quantiles.grad, rtol=1e-4, atol=1e-6)
+    assert all(p.grad is None for n, p in ours.named_parameters() if n != "quantiles")
+
+
+def test_eb_empty_batch():
+    ours, _ = _pair_eb(4, False)
+    ours.to(DEV).eval()
+    out, lik = ours(torch.zeros(0, 4, 2, 2, device=DEV))
+    assert out.shape == (0, 4, 2, 2) and lik.shape == (0, 4, 2, 2)
+
+
+# ------------------------------------------------------------------------------------------------ a5
+@pytest.mark.parametrize("yshape,sshape", [((3, 8, 1, 1), (3, 8, 4, 4)), ((4, 6, 4, 4), (4, 6, 4, 4)),
+                                           ((2, 5, 3, 7), (2, 5, 3, 7)), ((2, 4, 1, 1), (2, 4, 3, 5)),
+                                           ((2, 4, 1, 3), (2, 4, 2, 3))])
+def test_gc_forward_shapes(gc_pair, yshape, sshape):
+    ours, ref = gc_pair
+    torch.manual_seed(4)
+    scales = torch.exp(torch.empty(*sshape).uniform_(np.log(0.05), np.log(64)))
+    y = torch.randn(*yshape) * 3
+    y.view(-1)[0] = 800.0
+    ours.eval(), ref.eval()
+    yh, yl = ours(y.to(DEV), scales.to(DEV))
+    yh_r, yl_r = ref(y, scales)
+    refd = R.GaussianConditional(None).double().eval()
+    _, yl_d = refd(y.double(), scales.double())
+    assert yh.shape == yh_r.shape and yl.shape == yl_r.shape
+    assert torch.equal(yh.cpu(), yh_r)
+    assert_likelihood_close(yl, yl_r, want64=yl_d, what="GC eval")
+    C = sshape[1]
+    assert torch.allclose(ours.last_log_likelihood_sums.cpu().double(),
+                          torch.log(yl_r.double()).transpose(0, 1).reshape(C, -1).sum(1), rtol=2e-5, atol=1e-4)
+    ours.train(), ref.train()
+    noise = torch.rand(*yshape) - 0.5
+    yh, yl = ours(y.to(DEV), scales.to(DEV), noise=noise.to(DEV))
+    yh_r, yl_r = ref(y, scales, noise=noise)
+    assert torch.equal(yh.cpu(), yh_r)
+    assert_likelihood_close(yl, yl_r, what="GC train", rtol=2e-5)
+
+
+def test_gc_golden_and_means(gc_pair):
+    ours, ref = gc_pair
+    fx = load_golden()
+    ours.eval(), ref.eval()
+    yh, yl = ours(torch.from_numpy(fx["gc_y_bcast"]).to(DEV), torch.from_numpy(fx["gc_scales"]).to(DEV))
+    assert np.array_equal(yh.cpu().numpy(), fx["gc_yhat_bcast"])
+    assert_likelihood_close(yl, torch.from_numpy(fx["gc_lik_bcast"]), rtol=2e-5, what="GC golden")
+    torch.manual_seed(6)
+    y, sc, mu = torch.randn(2, 3, 4, 4) * 4, torch.rand(2, 3, 4, 4) * 3 + 0.05, torch.randn(2, 3, 4, 4)
+    yh, yl = ours(y.to(DEV), sc.to(DEV), means=mu.to(DEV))
+    yh_r, yl_r = ref(y, sc, means=mu)
+    assert torch.equal(yh.cpu(), yh_r)
+    assert_likelihood_close(yl, yl_r, rtol=2e-5, what="GC means")
+
+
+@pytest.mark.parametrize("yshape,sshape", [((3, 8, 1, 1), (3, 8, 4, 4)), ((4, 6, 4, 4), (4, 6, 4, 4)),
+                                           ((2, 4, 1, 1), (2, 4, 3, 5))])
+def test_gc_backward_matches_autograd(gc_pair, yshape, sshape):
+    ours, _ = gc_pair
+    ours.train()
+    refd = R.GaussianConditional(None).double().train()
+    torch.manual_seed(7)
+    C = sshape[1]
+    scales = torch.exp(torch.empty(*sshape).uniform_(np.log(0.05), np.log(30)))
+    y, noise = torch.randn(*yshape) * 3, torch.rand(*yshape) - 0.5
+    g_lik, g_out, w = torch.randn(*sshape), torch.randn(*yshape), torch.randn(C)
+    yd, sd = y.to(DEV).requires_grad_(True), scales.to(DEV).requires_grad_(True)
+    yh, yl = ours(yd, sd, noise=noise.to(DEV))
+    ((yl * g_lik.to(DEV)).sum() + (yh * g_out.to(DEV)).sum() + (ours.last_log_likelihood_sums * w.to(DEV)).sum()).backward()
+    y64, s64 = y.double().requires_grad_(True), scales.double().requires_grad_(True)
+    yh_r, yl_r = refd(y64, s64, noise=noise.double())
+    ln_r = torch.log(yl_r).transpose(0, 1).reshape(C, -1).sum(1)
+    ((yl_r * g_lik.double()).sum() + (yh_r * g_out.double()).sum() + (ln_r * w.double()).sum()).backward()
+    assert torch.allclose(yd.grad.cpu().double(), y64.grad, rtol=2e-3, atol=2e-5)
+    assert torch.allclose(sd.grad.cpu().double(), s64.grad, rtol=2e-3, atol=2e-5)
+
+
+def test_lnsum_op_forward_backward():
+    torch.manual_seed(8)
+    lik = (torch.rand(5, 7, 3, 3) * 0.9 + 1e-6)
+    ld = lik.to(DEV).requires_grad_(True)
+    s = mm.ops.channel_log_likelihood_sums(ld)
+    want = torch.log(lik.double()).transpose(0, 1).reshape(7, -1).sum(1)
+    assert torch.allclose(s.cpu().double(), want, rtol=1e-5)
+    w = torch.randn(7)
+    (s * w.to(DEV)).sum().backward()
+    assert torch.allclose(ld.grad.cpu(), (w.view(1, 7, 1, 1) / lik), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ a8
+GDN_SHAPES = [(2, 10, 6, 5), (1, 1, 16, 16), (2, 3, 32, 32), (3, 16, 8, 8), (2, 50, 16, 16), (1, 100, 8, 16),
+              (2, 33, 4, 4), (4, 300, 1, 1), (1, 128, 12, 12), (2, 17, 7, 9)]
+
+
+def _pair_gdn(C, inverse, seed=0, precision="fp32"):
+    g = torch.Generator().manual_seed(seed)
+    ref = R.GDN(C, inverse=inverse)
+    with torch.no_grad():
+        ref.gamma.add_(torch.rand(C, C, generator=g) * 0.05)
+        ref.beta.add_(torch.rand(C, generator=g) * 0.5)
+    ours = mm.GDN(C, inverse=inverse, precision=precision)
+    ours.load_state_dict(ref.state_dict())
+    return ours.to(DEV), ref
+
+
+@pytest.mark.parametrize("shape", GDN_SHAPES)
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_forward_fp32(shape, inverse):
+    """fp32 SIMT contraction: tolerance = fp32 summation-order noise over C terms (rtol 2e-5)."""
+    torch.manual_seed(9)
+    ours, ref = _pair_gdn(shape[1], inverse)
+    x = torch.randn(*shape)
+    y = ours(x.to(DEV))
+    assert torch.allclose(y.cpu(), ref(x), rtol=2e-5, atol=1e-6)
+
+
+def test_gdn_golden():
+    fx = load_golden()
+    for tag, inv in (("gdn", False), ("igdn", True)):
+        ours = mm.GDN(10, inverse=inv, precision="fp32")
+        with torch.no_grad():
+            ours.beta.copy_(torch.from_numpy(fx[f"{tag}_beta"]))
+            ours.gamma.copy_(torch.from_numpy(fx[f"{tag}_gamma"]))
+        y = ours.to(DEV)(torch.from_numpy(fx[f"{tag}_x"]).to(DEV))
+        assert np.allclose(y.cpu().numpy(), fx[f"{tag}_y"], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 10, 6, 5), (2, 3, 16, 16), (2, 50, 8, 8), (3, 33, 4, 4), (2, 128, 4, 4),
+                                   (5, 20, 1, 1), (1, 70, 9, 9)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_backward_fp32(shape, inverse):
+    torch.manual_seed(10)
+    C = shape[1]
+    ours, ref = _pair_gdn(C, inverse)
+    refd = R.GDN(C, inverse=inverse).double()
+    refd.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
+    x, g = torch.randn(*shape), torch.randn(*shape)
+    xd = x.to(DEV).requires_grad_(True)
+    (ours(xd) * g.to(DEV)).sum().backward()
+    x64 = x.double().requires_grad_(True)
+    (refd(x64) * g.double()).sum().backward()
+    assert torch.allclose(xd.grad.cpu().double(), x64.grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(ours.beta.grad.cpu().double(), refd.beta.grad, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(ours.gamma.grad.cpu().double(), refd.gamma.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_gdn_reparam_lower_bound_gradient():
+    """A.2 / A.5: below the bound the gradient passes only if it is negative."""
+    C = 4
+    ours, ref = _pair_gdn(C, False)
+    with torch.no_grad():
+        for m in (ours, ref):
+            m.beta[:2] = 1e-4  # below bound sqrt(1e-6 + 2^-36)
+            m.gamma[0, :] = -1.0
+    x, g = torch.randn(2, C, 3, 3), torch.randn(2, C, 3, 3)
+    (ours(x.to(DEV)) * g.to(DEV)).sum().backward()
+    (ref(x) * g).sum().backward()
+    assert torch.allclose(ours.beta.grad.cpu(), ref.beta.grad, rtol=1e-3, atol=1e-5)
+    assert torch.allclose(ours.gamma.grad.cpu(), ref.gamma.grad, rtol=1e-3, atol=1e-5)
+
+
+def test_gdn_full_size_properties():
+    """BASELINE config C2's largest layer (GDN(50) on 256^2) at batch 8: size-independent properties."""
+    torch.manual_seed(11)
+    C, B, H = 50, 8, 256
+    ours, _ = _pair_gdn(C, False)
+    x = torch.randn(B, C, H, H, device=DEV)
+    y = ours(x)
+    # (1) sample check against torch ops on the same device
+    beta, gamma = ours.beta_reparam(ours.beta), ours.gamma_reparam(ours.gamma)
+    sl = (slice(0, 2), slice(None), slice(100, 110), slice(None))
+    want = x[sl] * torch.rsqrt(torch.nn.functional.conv2d(x[sl] ** 2, gamma.reshape(C, C, 1, 1), beta))
+    assert torch.allclose(y[sl], want, rtol=2e-5, atol=1e-6)
+    # (2) odd symmetry and (3) batch independence
+    assert torch.equal(ours(-x), -y)
+    assert torch.equal(ours(x[3:5]), y[3:5])
+    # (4) scaling law: y(s x; s^2 beta, gamma) = y(x; beta, gamma)
+    y2 = mm.ops.gdn(3.0 * x, 9.0 * beta, gamma, False, "fp32")
+    assert torch.allclose(y2, y, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ a10-a12
+def test_build_indexes_bit_exact(gc_pair):
+    ours, ref = gc_pair
+    table = R.get_scale_table()
+    scales = torch.cat([torch.exp(torch.empty(20000).uniform_(np.log(0.01), np.log(400))), table,
+                        table * (1 + 1e-7), table * (1 - 1e-7),
+                        torch.tensor([0.0, -1.0, float("inf"), float("nan"), 0.11, 256.0])]).reshape(1, 1, -1)
+    assert torch.equal(ours.build_indexes(scales.to(DEV)).cpu(), ref.build_indexes(scales))
+    fx = load_golden()
+    assert np.array_equal(ours.build_indexes(torch.from_numpy(fx["gc_scales"]).to(DEV)).cpu().numpy(), fx["gc_idx"])
+
+
+def test_rans_golden_streams(gc_pair):
+    ours, _ = gc_pair
+    fx = load_golden()
+    for sym, idx, want in zip(fx["rans_sym"], fx["rans_idx"], fx["rans_bytes"]):
+        s = mm.ops.rans_encode(torch.from_numpy(sym).to(DEV).reshape(1, -1), torch.from_numpy(idx).to(DEV).reshape(1, -1),
+                               0, ours._quantized_cdf, ours._cdf_length, ours._offset)
+        assert s == [want.tobytes()]
+        back = mm.ops.rans_decode(s, torch.from_numpy(idx).to(DEV).reshape(1, -1), 0, sym.size, ours._quantized_cdf,
+                                  ours._cdf_length, ours._offset)
+        assert np.array_equal(back.cpu().numpy().reshape(-1), sym)
+
+
+@pytest.mark.parametrize("B,shape", [(1, (8, 1, 1)), (7, (128, 1, 1)), (64, (300, 1, 1)), (5, (12, 4, 4)),
+                                     (33, (3, 5, 7))])
+def test_gc_compress_bit_exact(gc_pair, B, shape):
+    ours, ref = gc_pair
+    torch.manual_seed(12)
+    scales = torch.exp(torch.empty(B, *shape).uniform_(np.log(0.05), np.log(64)))
+    y = torch.randn(B, *shape) * scales
+    esc = torch.rand(B, *shape) < 0.01  # 1 % outliers -> bypass coding
+    y[esc] = y[esc] * 40 + 300
+    idx_r = ref.build_indexes(scales)
+    idx = ours.build_indexes(scales.to(DEV))
+    assert torch.equal(idx.cpu(), idx_r)
+    ref.marshalling = "lean"
+    s_r = ref.compress(y, idx_r)
+    s = ours.compress(y.to(DEV), idx)
+    assert s == s_r
+    assert torch.equal(ours.decompress(s, idx).cpu(), ref.decompress(s_r, idx_r))
+    assert torch.equal(ours.decompress(s, idx).cpu(), torch.round(y))
+
+
+@pytest.mark.parametrize("B,C,hw", [(1, 4, (1, 1)), (64, 300, (1, 1)), (9, 32, (2, 3)), (256, 512, (1, 1))])
+def test_eb_compress_bit_exact(B, C, hw):
+    torch.manual_seed(13)
+    ours, ref = _pair_eb(C, True)
+    ours.update(), ref.update()
+    assert torch.equal(ours._quantized_cdf, ref._quantized_cdf)
+    ours.to(DEV)
+    z = torch.randn(B, C, *hw) * 6
+    z[0, 0] = 90.0
+    ref.marshalling = "lean"
+    s_r = ref.compress(z)
+    s = ours.compress(z.to(DEV))
+    assert s == s_r
+    zh = ours.decompress(s, hw)
+    assert torch.equal(zh.cpu(), ref.decompress(s_r, hw))
+    ours.eval()
+    assert torch.equal(zh, ours(z.to(DEV))[0]), "decompress(compress(z)) == eval-mode quantisation"
+
+
+def test_rans_error_paths(gc_pair):
+    ours, _ = gc_pair
+    with pytest.raises(ValueError, match="same size"):
+        ours.compress(torch.zeros(2, 4, 1, 1, device=DEV), torch.zeros(2, 4, 4, 4, dtype=torch.int32, device=DEV))
+    bad_idx = torch.full((1, 4, 1, 1), 99, dtype=torch.int32, device=DEV)
+    with pytest.raises(ValueError, match="malformed"):
+        ours.compress(torch.zeros(1, 4, 1, 1, device=DEV), bad_idx)
+    idx = torch.zeros(1, 64, 1, 1, dtype=torch.int32, device=DEV)
+    s = ours.compress(torch.zeros(1, 64, 1, 1, device=DEV), idx)
+    with pytest.raises(ValueError, match="corrupt|truncated"):
+        ours.decompress([s[0][:4]], idx)
+
+
+def test_rans_full_size_roundtrip(gc_pair):
+    """BASELINE config 5 upper end: 1024 images, and a shape-consistent 192 x 16 x 16 latent (49 152 symbols)."""
+    ours, _ = gc_pair
+    torch.manual_seed(14)
+    for B, shape in ((1024, (128, 1, 1)), (16, (192, 16, 16))):
+        scales = torch.exp(torch.empty(B, *shape, device=DEV).uniform_(np.log(0.05), np.log(64)))
+        y = torch.randn(B, *shape, device=DEV) * scales
+        idx = ours.build_indexes(scales)
+        s = ours.compress(y, idx)
+        assert torch.equal(ours.decompress(s, idx), torch.round(y))
+        ours.eval()
+        _, lik = ours(y, scales)
+        est_bits = float(-torch.log2(lik).sum())
+        actual_bits = 8 * sum(len(b) for b in s)
+        assert actual_bits >= est_bits * 0.95 and actual_bits <= est_bits * 1.10 + 64 * B, (actual_bits, est_bits)
+        # spot-check a few streams against the CPU oracle
+        cdf, ln, off = (t.cpu().numpy() for t in (ours._quantized_cdf, ours._cdf_length, ours._offset))
+        for i in (0, B // 2, B - 1):
+            want = native.encode_with_indexes_np(torch.round(y[i]).int().cpu().numpy(), idx[i].cpu().numpy(), cdf, ln, off)
+            assert s[i] == want
+
+
+# ------------------------------------------------------------------------------------------------ a1, a6, a7: wrappers
+CONFIGS = [(1, ("mono",), 8, 8), (2, ("rgb", "depth_euclidean", "normal", "semantic"), 12, 8),
+           (3, ("rgb", "depth_euclidean", "normal"), 14, 12), (4, ("rgb", "depth_euclidean", "normal", "semantic"), 13, 8)]
+
+
+@pytest.mark.parametrize("kind,tasks,l,c", CONFIGS)
+def test_wrapper_loss_parity_from_same_likelihoods(kind, tasks, l, c):
+    """RD-loss formulas in isolation: feed both implementations the SAME likelihoods and reconstructions."""
+    torch.manual_seed(20 + kind)
+    ours = mm.build_compressor(kind, tasks, l, c, lmbda=1e-2)
+    ref = orm.ReferenceCompressor(kind, tasks, l, c, lmbda=1e-2)
+    ref.load_state_dict(ours.state_dict())
+    if kind != 1:
+        with torch.no_grad():
+            lv = torch.randn(len(tasks)) * 0.3
+            ours.loss_balancer.log_vars.copy_(lv), ref.loss_balancer.log_vars.copy_(lv)
+    ours.to(DEV)
+    B, M, N = 2, ours.model["compressor"].M, c * len(tasks)
+    lik = {"y": torch.rand(B, M, 4, 4) * 0.9 + 1e-7, "z": torch.rand(B, N, 1, 1) * 0.9 + 1e-7}
+    batch = mm.synthetic_batch(tasks, B, size=32, seed=3)
+    x_hats = {t: torch.randn(B, mm.task_parameters[t]["out_channels"], 32, 32) for t in tasks}
+    lik_d = {k: v.to(DEV).requires_grad_(True) for k, v in lik.items()}
+    xh_d = {k: v.to(DEV).requires_grad_(True) for k, v in x_hats.items()}
+    loss, logs = ours.rate_distortion_loss({k: v.to(DEV) for k, v in batch.items()}, xh_d, lik_d, "val")
+    lik_r = {k: v.clone().requires_grad_(True) for k, v in lik.items()}
+    xh_r = {k: v.clone().requires_grad_(True) for k, v in x_hats.items()}
+    rec, l1 = ref.multitask_reconstruction_loss(batch, xh_r, "val")
+    comp, l2 = ref.multitask_compression_loss(lik_r, xh_r, "val")
+    want = ref.lmbda * rec + comp
+    assert abs(loss.item() - want.item()) <= 1e-5 * abs(want.item())
+    want_logs = {"val/rec_loss": rec, "val/compression_loss": comp, "val/loss": want, **l1, **l2}
+    assert set(logs) == set(want_logs)
+    for k, v in want_logs.items():
+        assert abs(float(logs[k]) - float(v)) <= 1e-5 * abs(float(v)) + 1e-7, k
+    loss.backward(), want.backward()
+    for k in lik:
+        assert torch.allclose(lik_d[k].grad.cpu(), lik_r[k].grad, rtol=1e-4, atol=1e-9), k
+    for k in x_hats:
+        assert torch.allclose(xh_d[k].grad.cpu(), xh_r[k].grad, rtol=1e-4, atol=1e-8), k
+    if kind != 1:
+        assert torch.allclose(ours.loss_balancer.log_vars.grad.cpu(), ref.loss_balancer.log_vars.grad, rtol=1e-4)
+    # reference-shaped entry points agree with the fused one
+    c2, _ = ours.multitask_compression_loss(lik_d, xh_d, "val")
+    r2, _ = ours.multitask_reconstruction_loss({k: v.to(DEV) for k, v in batch.items()}, xh_d, "val")
+    assert abs(c2.item() - comp.item()) <= 1e-5 * abs(comp.item()) and abs(r2.item() - rec.item()) <= 1e-5 * abs(rec.item())
+
+
+@pytest.mark.parametrize("kind,tasks,l,c", CONFIGS)
+def test_wrapper_end_to_end_vs_oracle(kind, tasks, l, c):
+    """Whole model at 256^2 (the reference's y (B,M,1,1) / scales (B,M,4,4) broadcast included).  Convolutions run
+    on different devices (cuDNN vs CPU) in the two arms, hence the looser tolerance on the scalar loss."""
+    torch.manual_seed(30 + kind)
+    ours = mm.build_compressor(kind, tasks, l, c, lmbda=1e-2)
+    ref = orm.ReferenceCompressor(kind, tasks, l, c, lmbda=1e-2).eval()
+    ref.load_state_dict(ours.state_dict())
+    ours.to(DEV).eval()
+    batch = mm.synthetic_batch(tasks, 2, size=256, seed=21)
+    bd = {k: v.to(DEV) for k, v in batch.items()}
+    with torch.backends.cudnn.flags(allow_tf32=False), torch.no_grad():
+        torch.backends.cuda.matmul.allow_tf32 = False
+        x_hats, lik = ours(bd)
+        loss, logs = ours.rate_distortion_loss(bd, x_hats, lik, "val")
+        want, want_logs = ref.rd_loss(batch, "val")
+    assert lik["y"].shape == (2, ours.model["compressor"].M, 4, 4) and lik["z"].shape[2:] == (1, 1)
+    assert all(x_hats[t].shape[-2:] == (256, 256) for t in tasks)
+    assert abs(loss.item() - want.item()) <= 5e-4 * abs(want.item())
+    for k in want_logs:
+        assert abs(float(logs[k]) - float(want_logs[k])) <= 2e-3 * abs(float(want_logs[k])) + 1e-6, k
+
+
+def test_train_step_gradients_vs_oracle():
+    """One -m 3 train step: gradients of a sample of parameters against the oracle's autograd (CPU)."""
+    torch.manual_seed(41)
+    tasks = ("rgb", "depth_euclidean", "normal")
+    ours = mm.build_compressor(3, tasks, 14, 12, lmbda=1e-2)
+    ref = orm.ReferenceCompressor(3, tasks, 14, 12, lmbda=1e-2).train()
+    ref.load_state_dict(ours.state_dict())
+    ours.to(DEV).train()
+    batch = mm.synthetic_batch(tasks, 2, size=256, seed=21)
+    bd = {k: v.to(DEV) for k, v in batch.items()}
+    nz = torch.rand(2, 36, 1, 1) - 0.5
+    ny = torch.rand(2, 14, 1, 1) - 0.5
+    # inject the same noise into both arms through the modules' test hook
+    co, cr = ours.model["compressor"], ref.model["compressor"]
+    eb_f, gc_f, eb_rf, gc_rf = (co.entropy_bottleneck.forward, co.gaussian_conditional.forward,
+                                cr.entropy_bottleneck.forward, cr.gaussian_conditional.forward)
+    co.entropy_bottleneck.forward = lambda x, training=None: eb_f(x, training, noise=nz.to(DEV))
+    co.gaussian_conditional.forward = lambda y, s, means=None, training=None: gc_f(y, s, means, training, noise=ny.to(DEV))
+    cr.entropy_bottleneck.forward = lambda x, training=None: eb_rf(x, training, noise=nz)
+    cr.gaussian_conditional.forward = lambda y, s, means=None, training=None: gc_rf(y, s, means, training, noise=ny)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        x_hats, lik = ours(bd)
+        loss, _ = ours.rate_distortion_loss(bd, x_hats, lik, "train")
+        loss.backward()
+    want, _ = ref.rd_loss(batch, "train")
+    want.backward()
+    assert abs(loss.item() - want.item()) <= 5e-4 * abs(want.item())
+    ref_params = dict(ref.named_parameters())
+    checked = 0
+    for name, p in ours.named_parameters():
+        if p.grad is None or name.endswith("quantiles"):
+            continue
+        g, w = p.grad.cpu(), ref_params[name].grad
+        denom = w.abs().max().item()
+        if denom < 1e-12:
+            continue
+        err = (g - w).abs().max().item() / denom
+        assert err < 2e-2, (name, err)
+        checked += 1
+    assert checked > 100
+
+
+def test_model_compress_decompress_roundtrip_and_module_parity():
+    """-m 2 at reduced resolution where y and scales have the same shape, so compress() is well defined
+    (at 256^2 the reference raises, Appendix B1 — checked below)."""
+    torch.manual_seed(42)
+    tasks = ("rgb", "depth_euclidean")
+    ours = mm.build_compressor(2, tasks, 12, 8, lmbda=1e-2)
+    ours.update_bottleneck_values()
+    ours.to(DEV).eval()
+    c = ours.model["compressor"]
+    x = torch.randn(3, 16, 64, 64, device=DEV)  # backbone input: y is 4x4, z is 1x1, scales 4x4
+    with torch.no_grad():
+        out = c.compress(x)
+        y = c.g_a(x)
+        z = c.h_a(torch.abs(y))
+    # module-level parity with the oracle on the SAME y, z
+    ref_eb, ref_gc = R.EntropyBottleneck(16), R.GaussianConditional(None)
+    ref_eb.load_state_dict({k: v.cpu() for k, v in c.entropy_bottleneck.state_dict().items()})
+    ref_gc.update_scale_table(R.get_scale_table())
+    ref_eb.marshalling = ref_gc.marshalling = "lean"
+    assert out["strings"][1] == ref_eb.compress(z.cpu())
+    with torch.no_grad():
+        z_hat = c.entropy_bottleneck.decompress(out["strings"][1], z.shape[-2:])
+        idx = c.gaussian_conditional.build_indexes(c.h_s(z_hat))
+    assert out["strings"][0] == ref_gc.compress(y.cpu(), idx.cpu())
+    with torch.no_grad():
+        rec = c.decompress(out["strings"], out["shape"])["x_hat"]
+        y_hat = c.gaussian_conditional.decompress(out["strings"][0], idx, z_hat.dtype)
+    assert torch.equal(y_hat, torch.round(y)) and rec.shape == x.shape
+    batch = mm.synthetic_batch(tasks, 1, size=256, seed=21, device=DEV)
+    with pytest.raises(ValueError, match="same size"):
+        ours.compress(batch)  # Appendix B1: y (B,M,1,1) vs indexes (B,M,4,4)
+
+
+def test_decompress_wrapper_matches_forward():
+    """MultiTaskCompressor.decompress (mtc.py:536-549) reproduces the eval forward's reconstruction."""
+    torch.manual_seed(43)
+    tasks = ("rgb", "depth_euclidean", "normal")
+    ours = mm.build_compressor(3, tasks, 15, 12, lmbda=1e-2)
+    ours.update_bottleneck_values()
+    ours.to(DEV).eval()
+    c = ours.model["compressor"]
+    with torch.no_grad():
+        z = torch.randn(2, 36, 1, 1, device=DEV) * 3
+        z_strings = c.entropy_bottleneck.compress(z)
+        z_hat = c.entropy_bottleneck.decompress(z_strings, (1, 1))
+        scales = c.h_s(z_hat)
+        idx = c.gaussian_conditional.build_indexes(scales)
+        y = torch.randn(2, 15, 4, 4, device=DEV) * scales
+        y_strings = c.gaussian_conditional.compress(y, idx)
+        x_hats = ours.decompress([y_strings, z_strings], (1, 1))
+        want = ours.forward_output_heads(torch.round(y))
+    assert all(torch.equal(x_hats[t], want[t]) for t in tasks)
+
+
+def test_launch_counter_moves():
+    before = mm.launch_count()
+    mm.GDN(4).to(DEV)(torch.randn(1, 4, 8, 8, device=DEV))
+    assert mm.launch_count() >= before + 3  # 2 reparam + 1 contraction

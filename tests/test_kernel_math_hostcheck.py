@@ -1,0 +1,156 @@
+"""CPU check of the kernels' per-element arithmetic: csrc/hd_math.cuh compiled for the host
+(tests/hostcheck) against the oracle.  This is the no-GPU safety net; the parity tests proper are in
+test_gpu_parity.py and call the CUDA library through the C ABI."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_likelihood_close, eb_double, fptr, hostcheck, load_golden, pack_eb, perturb_eb_
+from oracle import compressai_ref as R
+from oracle import native
+
+
+@pytest.fixture(scope="module")
+def hc():
+    return hostcheck()
+
+
+@pytest.fixture(scope="module")
+def gc():
+    m = R.GaussianConditional(None)
+    m.update_scale_table(R.get_scale_table())
+    return m
+
+
+@pytest.mark.parametrize("form", ["sign", "plain"])
+@pytest.mark.parametrize("perturbed", [False, True])
+def test_eb_forward_matches_oracle(hc, form, perturbed):
+    torch.manual_seed(0)
+    C, L = 7, 257
+    eb = R.EntropyBottleneck(C, likelihood_form=form)
+    if perturbed:
+        perturb_eb_(eb)
+    v = (torch.randn(C, 1, L) * 6).float()
+    v[0, 0, :4] = torch.tensor([80.0, -80.0, 0.0, 0.5])
+    want = eb.likelihood_lower_bound(eb._likelihood(v)).detach()
+    ebd = eb_double(eb)
+    want64 = ebd.likelihood_lower_bound(ebd._likelihood(v.double())).detach().reshape(C, L)
+    P = pack_eb(eb).numpy()
+    vn = v.reshape(C, L).contiguous().numpy()
+    lik = np.empty_like(vn)
+    hc.hc_eb_forward(fptr(vn), C, L, fptr(P), ctypes.c_float(1e-9), 0 if form == "sign" else 1, fptr(lik), None, None)
+    rtol = 1e-5 if form == "sign" else 2e-3  # the plain form cancels in the upper tail (A.3): looser by nature
+    assert_likelihood_close(torch.from_numpy(lik), want.reshape(C, L), rtol=rtol, floor_atol=5e-9, what=f"EB {form}",
+                            want64=want64 if form == "sign" else None)
+
+
+def test_eb_backward_matches_autograd(hc):
+    torch.manual_seed(1)
+    C, L = 5, 64
+    eb = perturb_eb_(R.EntropyBottleneck(C).double())
+    v = (torch.randn(C, 1, L, dtype=torch.float64) * 4).requires_grad_(True)
+    g_lik = torch.randn(C, 1, L, dtype=torch.float64)
+    lik = eb.likelihood_lower_bound(eb._likelihood(v))
+    (lik * g_lik).sum().backward()
+    names = []
+    for i in range(5):
+        names += [f"_matrix{i}", f"_bias{i}"] + ([f"_factor{i}"] if i < 4 else [])
+    want_gp = torch.cat([getattr(eb, n).grad.reshape(C, -1) for n in names], dim=1)
+    P = pack_eb(eb).float().numpy()
+    vn = v.detach().float().reshape(C, L).contiguous().numpy()
+    gl = g_lik.float().reshape(C, L).contiguous().numpy()
+    gv, gp = np.empty_like(vn), np.zeros((C, 58), dtype=np.float32)
+    hc.hc_eb_backward(fptr(vn), C, L, fptr(P), fptr(gl), ctypes.c_float(1e-9), 0, fptr(gv), fptr(gp))
+    assert np.allclose(gv, v.grad.reshape(C, L).numpy(), rtol=2e-3, atol=2e-6)
+    assert np.allclose(gp, want_gp.numpy(), rtol=2e-3, atol=1e-4)
+
+
+def test_gc_likelihood_and_grads(hc, gc):
+    torch.manual_seed(2)
+    n = 4096
+    scales = torch.exp(torch.empty(n).uniform_(np.log(0.05), np.log(64)))
+    y_hat = torch.round(torch.randn(n) * scales)
+    y_hat[:8] = torch.tensor([0, 1, -1, 40, -40, 1000, 0.5, -0.5])
+    want = gc.likelihood_lower_bound(gc._likelihood(y_hat, scales))
+    lik, dy, ds = (np.empty(n, dtype=np.float32) for _ in range(3))
+    hc.hc_gc_forward(fptr(y_hat.numpy()), fptr(scales.numpy()), ctypes.c_int64(n), ctypes.c_float(0.11),
+                     ctypes.c_float(1e-9), fptr(lik), fptr(dy), fptr(ds))
+    assert_likelihood_close(torch.from_numpy(lik), want, rtol=1e-5, what="GC")
+    # derivatives against float64 autograd of the oracle formula (noise-mode inputs, away from the bounds)
+    yv = (torch.randn(n, dtype=torch.float64) * 3).requires_grad_(True)
+    sv = torch.exp(torch.empty(n, dtype=torch.float64).uniform_(np.log(0.2), np.log(30))).requires_grad_(True)
+    gcd = R.GaussianConditional(None).double()
+    gcd._likelihood(yv, sv).sum().backward()
+    hc.hc_gc_forward(fptr(yv.detach().float().numpy()), fptr(sv.detach().float().numpy()), ctypes.c_int64(n),
+                     ctypes.c_float(0.11), ctypes.c_float(0.0), fptr(lik), fptr(dy), fptr(ds))
+    assert np.allclose(dy, yv.grad.numpy(), rtol=1e-3, atol=1e-6)
+    assert np.allclose(ds, sv.grad.numpy(), rtol=1e-3, atol=1e-6)
+
+
+def test_scale_index_matches_compare_count(hc, gc):
+    table = R.get_scale_table()
+    scales = torch.cat([torch.exp(torch.empty(5000).uniform_(np.log(0.01), np.log(400))), table, table * (1 + 1e-7),
+                        table * (1 - 1e-7), torch.tensor([0.0, -1.0, float("inf"), float("nan"), 0.11, 256.0])])
+    want = gc.build_indexes(scales).numpy()
+    got = np.empty(scales.numel(), dtype=np.int32)
+    hc.hc_scale_index(fptr(scales.numpy()), ctypes.c_int64(scales.numel()), fptr(table.numpy()), 64,
+                      ctypes.c_float(0.11), fptr(got))
+    assert np.array_equal(got, want)
+
+
+def test_philox_uniform_statistics(hc):
+    n = 200000
+    u = np.empty(n, dtype=np.float32)
+    hc.hc_philox(ctypes.c_uint64(21), ctypes.c_uint64(0), ctypes.c_int64(n), fptr(u))
+    assert u.min() >= -0.5 and u.max() < 0.5
+    assert abs(u.mean()) < 3e-3 and abs(u.var() - 1 / 12) < 2e-3
+    assert abs(np.corrcoef(u[:-1], u[1:])[0, 1]) < 1e-2
+    v = np.empty(n, dtype=np.float32)
+    hc.hc_philox(ctypes.c_uint64(21), ctypes.c_uint64(1000), ctypes.c_int64(n), fptr(v))
+    assert np.array_equal(u[1000:2000], v[:1000])  # offset = position in one stream (DP rank invariance)
+
+
+def _enc(hc, sym, idx, cdf, ln, off):
+    sym, idx = np.ascontiguousarray(sym, dtype=np.int32), np.ascontiguousarray(idx, dtype=np.int32)
+    cap = (sym.size * 52 + 31) // 32 + 20
+    out = np.empty(cap * 4, dtype=np.uint8)
+    n = hc.hc_rans_encode(fptr(sym), fptr(idx), ctypes.c_int64(sym.size), fptr(cdf), cdf.shape[0], cdf.shape[1],
+                          fptr(ln), fptr(off), fptr(out), ctypes.c_int64(cap))
+    assert n > 0, n
+    return out[:n].tobytes()
+
+
+def _dec(hc, b, idx, cdf, ln, off):
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    out = np.empty(idx.size, dtype=np.int32)
+    buf = np.frombuffer(b, dtype=np.uint8)
+    rc = hc.hc_rans_decode(fptr(buf), ctypes.c_int64(len(b)), fptr(idx), ctypes.c_int64(idx.size), fptr(cdf),
+                           cdf.shape[0], cdf.shape[1], fptr(ln), fptr(off), fptr(out))
+    assert rc == 0, rc
+    return out
+
+
+def test_rans_state_machine_bit_exact_on_golden(hc, gc):
+    fx = load_golden()
+    cdf = np.ascontiguousarray(gc._quantized_cdf.numpy())
+    ln, off = gc._cdf_length.numpy().copy(), gc._offset.numpy().copy()
+    for sym, idx, want in zip(fx["rans_sym"], fx["rans_idx"], fx["rans_bytes"]):
+        b = _enc(hc, sym, idx, cdf, ln, off)
+        assert b == want.tobytes()
+        assert np.array_equal(_dec(hc, b, idx, cdf, ln, off), sym)
+
+
+def test_rans_state_machine_random_vs_oracle(hc, gc):
+    rng = np.random.default_rng(5)
+    cdf = np.ascontiguousarray(gc._quantized_cdf.numpy())
+    ln, off = gc._cdf_length.numpy().copy(), gc._offset.numpy().copy()
+    for n in (2, 3, 17, 300, 2000):
+        idx = rng.integers(0, 64, n).astype(np.int32)
+        sym = np.round(rng.standard_normal(n) * R.get_scale_table().numpy()[idx] * 1.5).astype(np.int32)
+        esc = rng.random(n) < 0.05
+        sym[esc] = rng.integers(-2 ** 20, 2 ** 20, esc.sum())
+        want = native.encode_with_indexes_np(sym, idx, cdf, ln, off)
+        assert _enc(hc, sym, idx, cdf, ln, off) == want
+        assert np.array_equal(_dec(hc, want, idx, cdf, ln, off), sym)
