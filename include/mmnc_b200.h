@@ -48,11 +48,12 @@ extern "C" {
 #define MMNC_EB_FORM_SIGN 0  /* CompressAI 1.2.x: |sigmoid(s*up) - sigmoid(s*lo)|, s = -sign(lo+up) */
 #define MMNC_EB_FORM_PLAIN 1 /* later releases: sigmoid(up) - sigmoid(lo) */
 
-/* precision of the GDN channel contraction */
-#define MMNC_GDN_FP32 0  /* SIMT fp32 FMA */
-#define MMNC_GDN_TF32 1  /* tcgen05 kind::tf32, single pass */
-#define MMNC_GDN_3XTF32 2 /* tcgen05 kind::tf32, hi/lo split (fp32-class accuracy) */
-#define MMNC_GDN_AUTO 3  /* library picks: tensor cores where the shape allows, SIMT otherwise */
+/* arithmetic the caller accepts for the GDN channel contraction.  Tensor cores (tcgen05) are used when the shape
+ * suits the kernel in that arithmetic; all other shapes run on the fp32 SIMT kernel (at least as accurate). */
+#define MMNC_GDN_FP32 0  /* fp32 FMA only */
+#define MMNC_GDN_TF32 1  /* tcgen05 kind::tf32, single pass (x^2 and gamma rounded to tf32) */
+#define MMNC_GDN_3XTF32 2 /* tcgen05 kind::tf32, hi/lo split in three passes (fp32-class accuracy) */
+#define MMNC_GDN_AUTO 3  /* = MMNC_GDN_3XTF32 */
 
 /* ---------------------------------------------------------------------------------------------------------
  * Library state

@@ -40,7 +40,7 @@ size_t gdn_simt_backward_workspace(int64_t, int64_t, int64_t);
 int gdn_simt_backward(const float *, const float *, int64_t, int64_t, int64_t, const float *, const float *, int,
                       float *, float *, float *, void *, size_t, cudaStream_t);
 // gdn_tc.cu
-bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW);
+bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision);
 int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const float *, const float *, int, int, float *, cudaStream_t);
 
 }  // namespace mmnc
@@ -59,17 +59,11 @@ extern "C" int mmnc_gdn_forward(const float *x, int64_t B, int64_t C, int64_t HW
     if (B * C * HW == 0) return MMNC_OK;
     MMNC_REQUIRE(x && beta && gamma && y, "gdn_forward: null pointer");
     MMNC_REQUIRE(C <= 8192, "gdn_forward: C = %lld too large", (long long)C);
-    const bool tc_ok = gdn_tc_supported(B, C, HW);
-    if (precision == MMNC_GDN_TF32 || precision == MMNC_GDN_3XTF32) {
-        if (!tc_ok) {
-            set_error("gdn_forward: tensor-core path does not take B=%lld C=%lld HW=%lld", (long long)B, (long long)C,
-                      (long long)HW);
-            return MMNC_ERR_UNSUPPORTED;
-        }
-        return gdn_tc_forward(x, B, C, HW, beta, gamma, inverse, precision, y, as_stream(stream));
-    }
-    if (precision == MMNC_GDN_AUTO && tc_ok)
-        return gdn_tc_forward(x, B, C, HW, beta, gamma, inverse, MMNC_GDN_3XTF32, y, as_stream(stream));
+    // `precision` names the arithmetic the caller accepts.  Tensor cores are used when the shape suits the tcgen05
+    // kernel in that arithmetic; everything else runs on the fp32 SIMT kernel, which is at least as accurate.
+    const int want = (precision == MMNC_GDN_AUTO) ? MMNC_GDN_3XTF32 : precision;
+    if (want != MMNC_GDN_FP32 && gdn_tc_supported(B, C, HW, want))
+        return gdn_tc_forward(x, B, C, HW, beta, gamma, inverse, want, y, as_stream(stream));
     return gdn_simt_forward(x, B, C, HW, beta, gamma, inverse, y, as_stream(stream));
 }
 

@@ -26,10 +26,10 @@ eb_forward_kernel(const float *__restrict__ x, int64_t B, int64_t C, int64_t S, 
                   const float *__restrict__ medians, int noise_mode, const float *__restrict__ noise,
                   uint64_t seed, uint64_t offset, float bound, int form, float *__restrict__ out,
                   float *__restrict__ lik, float *__restrict__ lnsum) {
-    __shared__ float P[EB_NP];
+    __shared__ double P[EB_NP];  // float64 forward, see hd_math.cuh
     __shared__ float red[32];
     const int64_t c = blockIdx.x;
-    if (threadIdx.x < EB_NP) P[threadIdx.x] = eb_transform(threadIdx.x, params[c * EB_NP + threadIdx.x]);
+    if (threadIdx.x < EB_NP) P[threadIdx.x] = eb_transform_d(threadIdx.x, params[c * EB_NP + threadIdx.x]);
     __syncthreads();
     const float med = medians[c];
     const int64_t n = B * S;
@@ -42,9 +42,10 @@ eb_forward_kernel(const float *__restrict__ x, int64_t B, int64_t C, int64_t S, 
         else if (noise_mode == MMNC_QUANT_NOISE_PHILOX) v = xv + philox_uniform_centered(seed, (uint64_t)a + offset);
         else if (noise_mode == MMNC_QUANT_NOISE_GIVEN) v = xv + noise[a];
         else v = xv;
-        const float lower = eb_logits<false>(P, v - 0.5f, nullptr);
-        const float upper = eb_logits<false>(P, v + 0.5f, nullptr);
-        float l = eb_likelihood(lower, upper, form);
+        // the reference forms v - 0.5 / v + 0.5 in fp32 before the MLP; keep that rounding
+        const double lower = eb_logits_d(P, (double)(v - 0.5f));
+        const double upper = eb_logits_d(P, (double)(v + 0.5f));
+        float l = eb_likelihood_d(lower, upper, form);
         if (bound > 0.f) l = max_nan(l, bound);
         out[a] = v;
         lik[a] = l;

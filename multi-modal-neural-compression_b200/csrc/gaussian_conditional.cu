@@ -37,7 +37,7 @@ gc_forward_kernel(const float *__restrict__ y, const float *__restrict__ scales,
         else if (noise_mode == MMNC_QUANT_NOISE_PHILOX) v = yv + philox_uniform_centered(seed, (uint64_t)yi + offset);
         else if (noise_mode == MMNC_QUANT_NOISE_GIVEN) v = yv + noise[yi];
         else v = yv;
-        float l = gc_likelihood(v, m, scales[ai], scale_bound);
+        float l = gc_likelihood_d(v, m, scales[ai], scale_bound);
         if (lik_bound > 0.f) l = max_nan(l, lik_bound);
         lik[ai] = l;
         if (!bcast || s == 0) y_hat[yi] = v;

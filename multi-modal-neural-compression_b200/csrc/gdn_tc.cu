@@ -1,14 +1,278 @@
-// K4 (tensor-core path): GDN / IGDN channel contraction on tcgen05 (placeholder until the kernel lands).
+// K4 (tensor-core path): GDN / IGDN forward with the channel contraction on tcgen05.
+//
+//   norm[p][i] = beta_i + sum_j x[p][j]^2 * gamma[i][j]        D[128 x N] (+)= A[128 x K] * B[K x N]
+//
+// One CTA = 128 threads = one tile of 128 flattened pixels at a time (persistent loop over tiles).
+//   A = x^2 (tf32)  : written by the threads straight into TENSOR MEMORY with tcgen05.st — thread t owns pixel t,
+//                     i.e. TMEM lane t; column k holds channel k.  The global loads behind it are fully coalesced
+//                     (a warp reads 32 consecutive pixels of one channel) and no shared-memory operand layout has
+//                     to be produced for the NCHW (pixel-contiguous = "MN-major") input.
+//   B = gamma (tf32): staged ONCE per CTA in shared memory in the canonical K-major no-swizzle core-matrix layout
+//                     (8 rows x 16 bytes per core matrix), consumed through a shared-memory matrix descriptor.
+//   D = fp32 accumulator in TMEM, read back with tcgen05.ld for the epilogue y = x * (beta + D)^(-+1/2).
+// kind::tf32, cta_group::1, M = 128, N = C rounded up to 16, K = 8 per instruction (C rounded up to 8).
+//
+// Precision modes: MMNC_GDN_TF32 = one pass (x^2 and gamma rounded to tf32 with round-to-nearest);
+// MMNC_GDN_3XTF32 = hi/lo split of both operands, three passes (hi*hi + lo*hi + hi*lo), fp32-class accuracy.
+// The tensor pipe has so much headroom over HBM here that even three passes stay memory-bound.
 #include "common.cuh"
 
 namespace mmnc {
 
-bool gdn_tc_supported(int64_t, int64_t, int64_t) { return false; }
+namespace tc {
 
-int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const float *, const float *, int, int, float *,
-                   cudaStream_t) {
-    set_error("gdn_tc_forward: not built");
-    return MMNC_ERR_UNSUPPORTED;
+constexpr int TILE_M = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
+// shared-memory matrix descriptor: K-major, no swizzle.  Core matrix = 8 rows x 16 B stored as 128 contiguous
+// bytes; LBO = byte distance between core matrices adjacent in K, SBO = between 8-row groups (both >> 4).
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version: Blackwell
+    return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+
+// instruction descriptor for kind::tf32: D = F32, A = B = TF32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+struct Geometry {
+    int C, Kp, Np;        // channels, K padded to 8, N padded to 16
+    int a_cols, d_col;    // TMEM columns used by A (hi [+ lo]) and first column of D
+    uint32_t tmem_cols;   // power of two >= 32
+    size_t b_bytes;       // one B operand (hi); the lo copy follows when 3xTF32
+};
+
+}  // namespace tc
+
+template <bool k3x>
+__global__ void __launch_bounds__(tc::TILE_M)
+gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const float *__restrict__ beta,
+                      const float *__restrict__ gamma, int inverse, float *__restrict__ y, tc::Geometry geo) {
+    using namespace tc;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    float *Bs_hi = reinterpret_cast<float *>(smem);
+    float *Bs_lo = reinterpret_cast<float *>(smem + geo.b_bytes);
+    float *beta_s = reinterpret_cast<float *>(smem + geo.b_bytes * (k3x ? 2 : 1));
+    const int C = geo.C, Kp = geo.Kp, Np = geo.Np;
+    const int warp = threadIdx.x >> 5;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, geo.tmem_cols);
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    // B operand: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]) (zero padded)
+    const int kcores = Kp >> 2;
+    for (int idx = threadIdx.x; idx < Np * Kp; idx += TILE_M) {
+        const int n = idx / Kp, k = idx - n * Kp;
+        const float g = (n < C && k < C) ? gamma[(int64_t)n * C + k] : 0.f;
+        const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
+        const uint32_t hi = to_tf32(g);
+        reinterpret_cast<uint32_t *>(Bs_hi)[off] = hi;
+        if (k3x) reinterpret_cast<uint32_t *>(Bs_lo)[off] = to_tf32(g - __uint_as_float(hi));
+    }
+    for (int i = threadIdx.x; i < Np; i += TILE_M) beta_s[i] = (i < C) ? beta[i] : 1.f;
+    fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t a_hi = 0, a_lo = (uint32_t)Kp, d_col = (uint32_t)geo.d_col;
+    const uint32_t idesc = make_idesc(Np);
+    const uint32_t lbo = 128, sbo = (uint32_t)kcores * 128;
+    const uint64_t desc_hi = make_b_desc(smem_u32(Bs_hi), lbo, sbo);
+    const uint64_t desc_lo = make_b_desc(smem_u32(Bs_lo), lbo, sbo);
+    uint32_t parity = 0;
+
+    for (int64_t tile = blockIdx.x; tile * TILE_M < NP; tile += gridDim.x) {
+        const int64_t P = tile * TILE_M + threadIdx.x;
+        const bool valid = P < NP;
+        const int64_t b = valid ? P / HW : 0;
+        const int64_t base = b * C * HW + (valid ? P - b * HW : 0);
+        // ---- A operand: x^2 -> tf32 -> TMEM (lane = pixel, column = channel)
+        for (int c0 = 0; c0 < Kp; c0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (valid && c0 + j < C) ? x[base + (int64_t)(c0 + j) * HW] : 0.f;
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float sq = v[j] * v[j];
+                hi[j] = to_tf32(sq);
+                if (k3x) lo[j] = to_tf32(sq - __uint_as_float(hi[j]));
+            }
+            tmem_st8(lane_base + a_hi + c0, hi);
+            if (k3x) tmem_st8(lane_base + a_lo + c0, lo);
+        }
+        tmem_st_wait();
+        fence_before();
+        __syncthreads();
+        // ---- MMA: one thread issues Kp/8 (x3) instructions, then commits to the mbarrier
+        if (threadIdx.x == 0) {
+            fence_after();
+            uint32_t acc = 0;
+            for (int ks = 0; ks < (Kp >> 3); ++ks) {
+                const uint64_t koff = (uint64_t)((ks * 256) >> 4);  // two core matrices (8 tf32) along K
+                mma_tf32_ts(tmem_base + d_col, tmem_base + a_hi + ks * 8, desc_hi + koff, idesc, acc);
+                acc = 1;
+                if (k3x) {
+                    mma_tf32_ts(tmem_base + d_col, tmem_base + a_lo + ks * 8, desc_hi + koff, idesc, 1);
+                    mma_tf32_ts(tmem_base + d_col, tmem_base + a_hi + ks * 8, desc_lo + koff, idesc, 1);
+                }
+            }
+            mma_commit(&mbar);
+        }
+        mbar_wait(&mbar, parity);
+        parity ^= 1;
+        fence_after();
+        // ---- epilogue: y = x * (beta + D)^(-+1/2); thread t writes pixel t of every channel (coalesced per warp)
+        for (int n0 = 0; n0 < Np; n0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(lane_base + d_col + n0, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int i = n0 + j;
+                    if (i < C) {
+                        const int64_t a = base + (int64_t)i * HW;
+                        const float n = beta_s[i] + __uint_as_float(r[j]);
+                        const float rt = sqrtf(n);
+                        y[a] = x[a] * (inverse ? rt : 1.f / rt);
+                    }
+                }
+            }
+        }
+        fence_before();
+        __syncthreads();  // every lane has drained D before the next tile overwrites A / D
+        fence_after();
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, geo.tmem_cols);
+}
+
+static bool tc_geometry(int64_t C, bool k3x, tc::Geometry *g) {
+    if (C < 8 || C > 256) return false;
+    g->C = (int)C;
+    g->Kp = (int)((C + 7) / 8 * 8);
+    g->Np = (int)((C + 15) / 16 * 16);
+    g->a_cols = g->Kp * (k3x ? 2 : 1);
+    g->d_col = g->a_cols;
+    const int need = g->a_cols + g->Np;
+    if (need > 512) return false;
+    uint32_t cols = 32;
+    while ((int)cols < need) cols <<= 1;
+    g->tmem_cols = cols;
+    g->b_bytes = ((size_t)g->Np * g->Kp * sizeof(float) + 127) / 128 * 128;
+    if (g->b_bytes * (k3x ? 2 : 1) + sizeof(float) * g->Np + 1024 > 227 * 1024) return false;  // gamma must fit smem
+    return true;
+}
+
+bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision) {
+    tc::Geometry g;
+    // small problems stay on the SIMT kernel: a tile is 128 pixels and the B operand is staged once per CTA
+    return tc_geometry(C, precision == MMNC_GDN_3XTF32, &g) && C >= 16 && B * HW >= 4096;
+}
+
+int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta, const float *gamma,
+                   int inverse, int precision, float *y, cudaStream_t s) {
+    tc::Geometry g;
+    const bool k3x = (precision == MMNC_GDN_3XTF32);
+    if (!tc_geometry(C, k3x, &g)) {
+        set_error("gdn_tc_forward: C = %lld not supported by the tensor-core path", (long long)C);
+        return MMNC_ERR_UNSUPPORTED;
+    }
+    const int64_t NP = B * HW;
+    const int64_t tiles = (NP + tc::TILE_M - 1) / tc::TILE_M;
+    size_t smem = g.b_bytes * (k3x ? 2 : 1) + sizeof(float) * g.Np;
+    // co-resident CTAs per SM are bounded by TMEM (512 columns): pad the shared-memory request so the hardware
+    // never schedules a CTA that would then spin inside tcgen05.alloc
+    const int max_ctas = 512 / (int)g.tmem_cols;
+    const size_t smem_cap = 227 * 1024;
+    const size_t min_smem = smem_cap / (size_t)(max_ctas + 1) + 1;
+    if (smem < min_smem && max_ctas < 8) smem = min_smem;
+    smem = (smem + 127) / 128 * 128;
+    if (smem > smem_cap) {
+        set_error("gdn_tc_forward: gamma does not fit shared memory for C = %lld", (long long)C);
+        return MMNC_ERR_UNSUPPORTED;
+    }
+    auto kernel = k3x ? gdn_tc_forward_kernel<true> : gdn_tc_forward_kernel<false>;
+    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (int64_t)sm_count() * (max_ctas < 4 ? max_ctas : 4);
+    if (grid > tiles) grid = tiles;
+    kernel<<<(unsigned)grid, tc::TILE_M, smem, s>>>(x, NP, HW, beta, gamma, inverse, y, g);
+    return after_launch(k3x ? "gdn_tc_forward_kernel<3xtf32>" : "gdn_tc_forward_kernel<tf32>");
 }
 
 }  // namespace mmnc
