@@ -84,6 +84,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one MUFU.RSQ (<= 2 ulp); n >= beta_min > 0 so flushing denormals is harmless.  torch's CUDA rsqrt is the same op.
+__device__ __forceinline__ float fast_rsqrt(float v) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t to_tf32(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -115,27 +122,108 @@ struct Geometry {
 
 }  // namespace tc
 
-template <bool k3x>
+// One tile: 128 pixels x all channels.  kFull = the tile has no out-of-range pixel (no per-element predicates).
+// KP8 = Kp / 8 is a template parameter so that the pixel's x values stay in registers (fully unrolled): they are
+// loaded from HBM once, squared into the A operand, and reused by the epilogue — 8 B/element of traffic, the
+// algorithmic minimum.  kBetaInMma: when C is not a multiple of 8 the K padding is free, so one padded A column
+// is the constant 1 and the matching B row holds beta: the accumulator comes back as beta + sum gamma x^2.
+template <bool k3x, int KP8, bool kBetaInMma, bool kFull>
+__device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float *__restrict__ yb, int64_t HW, int C,
+                                            bool inverse, bool valid, const float *beta_s, uint32_t tmem_base, uint32_t lane_base,
+                                            uint32_t d_col, uint64_t desc_hi, uint64_t desc_lo, uint32_t idesc,
+                                            uint64_t *mbar, uint32_t parity) {
+    using namespace tc;
+    constexpr int Kp = KP8 * 8;
+    constexpr int NP16 = (KP8 + 1) / 2;  // Np / 16
+    constexpr uint32_t a_hi = 0, a_lo = (uint32_t)Kp;
+    // ---- all of the pixel's channels in flight at once (one DRAM round trip per tile), kept in registers.
+    // Padded channels (c >= C) re-read the last real channel: their B rows are zero, so any finite value works.
+    float xv[Kp];
+#pragma unroll
+    for (int c = 0; c < Kp; ++c) {
+        const int cc = (c < Kp - 8) ? c : ((c < C) ? c : C - 1);
+        xv[c] = (kFull || valid) ? __ldcs(xb + (int64_t)cc * HW) : 0.f;
+    }
+    // ---- A operand: x^2 -> tf32 -> TMEM (lane = pixel, column = channel)
+#pragma unroll
+    for (int c0 = 0; c0 < Kp; c0 += 8) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float sq = xv[c0 + j] * xv[c0 + j];
+            if (kBetaInMma && c0 + j == Kp - 1) sq = 1.f;  // the constant column that picks up beta
+            hi[j] = to_tf32(sq);
+            if (k3x) lo[j] = to_tf32(sq - __uint_as_float(hi[j]));
+        }
+        tmem_st8(lane_base + a_hi + c0, hi);
+        if (k3x) tmem_st8(lane_base + a_lo + c0, lo);
+    }
+    tmem_st_wait();
+    fence_before();
+    __syncthreads();
+    // ---- MMA: one thread issues Kp/8 (x3) instructions, then commits to the mbarrier
+    if (threadIdx.x == 0) {
+        fence_after();
+#pragma unroll
+        for (int ks = 0; ks < KP8; ++ks) {
+            const uint64_t koff = (uint64_t)((ks * 256) >> 4);  // two core matrices (8 tf32) along K
+            mma_tf32_ts(tmem_base + d_col, tmem_base + a_hi + ks * 8, desc_hi + koff, idesc, ks > 0 ? 1u : 0u);
+            if (k3x) {
+                mma_tf32_ts(tmem_base + d_col, tmem_base + a_lo + ks * 8, desc_hi + koff, idesc, 1);
+                mma_tf32_ts(tmem_base + d_col, tmem_base + a_hi + ks * 8, desc_lo + koff, idesc, 1);
+            }
+        }
+        mma_commit(mbar);
+    }
+    mbar_wait(mbar, parity);
+    fence_after();
+    // ---- epilogue: y = x * n^(-+1/2) with n = beta + D; thread t writes pixel t of every channel
+#pragma unroll
+    for (int q = 0; q < NP16; ++q) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + d_col + q * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = q * 16 + j;
+            if (i < Kp) {
+                float n = __uint_as_float(r[j]);
+                if (!kBetaInMma) n += beta_s[i];
+                const float rs = fast_rsqrt(n);
+                const float out = xv[i] * (inverse ? n * rs : rs);
+                const bool ok = (kFull || valid) && (i < Kp - 8 || i < C);
+                if (ok) __stcs(yb + (int64_t)i * HW, out);
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();  // every lane has drained D before the next tile overwrites A / D
+    fence_after();
+}
+
+template <bool k3x, int KP8, bool kBetaInMma>
 __global__ void __launch_bounds__(tc::TILE_M)
 gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const float *__restrict__ beta,
-                      const float *__restrict__ gamma, int inverse, float *__restrict__ y, tc::Geometry geo) {
+                      const float *__restrict__ gamma, int inverse, float *__restrict__ y, int C, int Np, int d_col_i,
+                      uint32_t tmem_cols, uint32_t b_bytes) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
     float *Bs_hi = reinterpret_cast<float *>(smem);
-    float *Bs_lo = reinterpret_cast<float *>(smem + geo.b_bytes);
-    float *beta_s = reinterpret_cast<float *>(smem + geo.b_bytes * (k3x ? 2 : 1));
-    const int C = geo.C, Kp = geo.Kp, Np = geo.Np;
+    float *Bs_lo = reinterpret_cast<float *>(smem + b_bytes);
+    float *beta_s = reinterpret_cast<float *>(smem + b_bytes * (k3x ? 2 : 1));
+    constexpr int Kp = KP8 * 8;
     const int warp = threadIdx.x >> 5;
 
-    if (warp == 0) tmem_alloc(&tmem_base_s, geo.tmem_cols);
+    if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
-    // B operand: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]) (zero padded)
-    const int kcores = Kp >> 2;
+    // B operand: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]) (zero padded; row k = Kp-1 holds beta when kBetaInMma)
+    constexpr int kcores = Kp >> 2;
     for (int idx = threadIdx.x; idx < Np * Kp; idx += TILE_M) {
         const int n = idx / Kp, k = idx - n * Kp;
-        const float g = (n < C && k < C) ? gamma[(int64_t)n * C + k] : 0.f;
+        float g = (n < C && k < C) ? gamma[(int64_t)n * C + k] : 0.f;
+        if (kBetaInMma && k == Kp - 1) g = (n < C) ? beta[n] : 1.f;
         const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
         const uint32_t hi = to_tf32(g);
         reinterpret_cast<uint32_t *>(Bs_hi)[off] = hi;
@@ -148,7 +236,7 @@ gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const
     fence_after();
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t a_hi = 0, a_lo = (uint32_t)Kp, d_col = (uint32_t)geo.d_col;
+    const uint32_t d_col = (uint32_t)d_col_i;
     const uint32_t idesc = make_idesc(Np);
     const uint32_t lbo = 128, sbo = (uint32_t)kcores * 128;
     const uint64_t desc_hi = make_b_desc(smem_u32(Bs_hi), lbo, sbo);
@@ -157,73 +245,24 @@ gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const
 
     for (int64_t tile = blockIdx.x; tile * TILE_M < NP; tile += gridDim.x) {
         const int64_t P = tile * TILE_M + threadIdx.x;
+        const bool full = (tile + 1) * TILE_M <= NP;
         const bool valid = P < NP;
         const int64_t b = valid ? P / HW : 0;
         const int64_t base = b * C * HW + (valid ? P - b * HW : 0);
-        // ---- A operand: x^2 -> tf32 -> TMEM (lane = pixel, column = channel)
-        for (int c0 = 0; c0 < Kp; c0 += 8) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (valid && c0 + j < C) ? x[base + (int64_t)(c0 + j) * HW] : 0.f;
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float sq = v[j] * v[j];
-                hi[j] = to_tf32(sq);
-                if (k3x) lo[j] = to_tf32(sq - __uint_as_float(hi[j]));
-            }
-            tmem_st8(lane_base + a_hi + c0, hi);
-            if (k3x) tmem_st8(lane_base + a_lo + c0, lo);
-        }
-        tmem_st_wait();
-        fence_before();
-        __syncthreads();
-        // ---- MMA: one thread issues Kp/8 (x3) instructions, then commits to the mbarrier
-        if (threadIdx.x == 0) {
-            fence_after();
-            uint32_t acc = 0;
-            for (int ks = 0; ks < (Kp >> 3); ++ks) {
-                const uint64_t koff = (uint64_t)((ks * 256) >> 4);  // two core matrices (8 tf32) along K
-                mma_tf32_ts(tmem_base + d_col, tmem_base + a_hi + ks * 8, desc_hi + koff, idesc, acc);
-                acc = 1;
-                if (k3x) {
-                    mma_tf32_ts(tmem_base + d_col, tmem_base + a_lo + ks * 8, desc_hi + koff, idesc, 1);
-                    mma_tf32_ts(tmem_base + d_col, tmem_base + a_hi + ks * 8, desc_lo + koff, idesc, 1);
-                }
-            }
-            mma_commit(&mbar);
-        }
-        mbar_wait(&mbar, parity);
+        if (full)
+            gdn_tc_tile<k3x, KP8, kBetaInMma, true>(x + base, y + base, HW, C, inverse != 0, true, beta_s, tmem_base, lane_base,
+                                                              d_col, desc_hi, desc_lo, idesc, &mbar, parity);
+        else
+            gdn_tc_tile<k3x, KP8, kBetaInMma, false>(x + base, y + base, HW, C, inverse != 0, valid, beta_s, tmem_base,
+                                                               lane_base, d_col, desc_hi, desc_lo, idesc, &mbar, parity);
         parity ^= 1;
-        fence_after();
-        // ---- epilogue: y = x * (beta + D)^(-+1/2); thread t writes pixel t of every channel (coalesced per warp)
-        for (int n0 = 0; n0 < Np; n0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(lane_base + d_col + n0, r);
-            tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int i = n0 + j;
-                    if (i < C) {
-                        const int64_t a = base + (int64_t)i * HW;
-                        const float n = beta_s[i] + __uint_as_float(r[j]);
-                        const float rt = sqrtf(n);
-                        y[a] = x[a] * (inverse ? rt : 1.f / rt);
-                    }
-                }
-            }
-        }
-        fence_before();
-        __syncthreads();  // every lane has drained D before the next tile overwrites A / D
-        fence_after();
     }
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, geo.tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 static bool tc_geometry(int64_t C, bool k3x, tc::Geometry *g) {
-    if (C < 8 || C > 256) return false;
+    if (C < 8 || C > 128) return false;  // the pixel's channels live in registers: C <= 128
     g->C = (int)C;
     g->Kp = (int)((C + 7) / 8 * 8);
     g->Np = (int)((C + 15) / 16 * 16);
@@ -267,11 +306,31 @@ int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float
         set_error("gdn_tc_forward: gamma does not fit shared memory for C = %lld", (long long)C);
         return MMNC_ERR_UNSUPPORTED;
     }
-    auto kernel = k3x ? gdn_tc_forward_kernel<true> : gdn_tc_forward_kernel<false>;
+    using Kernel = void (*)(const float *, int64_t, int64_t, const float *, const float *, int, float *, int, int, int,
+                            uint32_t, uint32_t);
+    Kernel kernel = nullptr;
+    const bool beta_in_mma = (C % 8) != 0;
+#define MMNC_TC_CASE(N)                                                                                        \
+    case N:                                                                                                    \
+        if (k3x) kernel = beta_in_mma ? (Kernel)gdn_tc_forward_kernel<true, N, true> : (Kernel)gdn_tc_forward_kernel<true, N, false>;   \
+        else     kernel = beta_in_mma ? (Kernel)gdn_tc_forward_kernel<false, N, true> : (Kernel)gdn_tc_forward_kernel<false, N, false>; \
+        break;
+    switch (g.Kp / 8) {
+        MMNC_TC_CASE(2) MMNC_TC_CASE(3) MMNC_TC_CASE(4) MMNC_TC_CASE(5) MMNC_TC_CASE(6) MMNC_TC_CASE(7) MMNC_TC_CASE(8)
+        MMNC_TC_CASE(9) MMNC_TC_CASE(10) MMNC_TC_CASE(11) MMNC_TC_CASE(12) MMNC_TC_CASE(13) MMNC_TC_CASE(14)
+        MMNC_TC_CASE(15) MMNC_TC_CASE(16)
+        default: break;
+    }
+#undef MMNC_TC_CASE
+    if (kernel == nullptr) {
+        set_error("gdn_tc_forward: no kernel instance for C = %lld", (long long)C);
+        return MMNC_ERR_UNSUPPORTED;
+    }
     MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = (int64_t)sm_count() * (max_ctas < 4 ? max_ctas : 4);
     if (grid > tiles) grid = tiles;
-    kernel<<<(unsigned)grid, tc::TILE_M, smem, s>>>(x, NP, HW, beta, gamma, inverse, y, g);
+    kernel<<<(unsigned)grid, tc::TILE_M, smem, s>>>(x, NP, HW, beta, gamma, inverse, y, g.C, g.Np, g.d_col, g.tmem_cols,
+                                                    (uint32_t)g.b_bytes);
     return after_launch(k3x ? "gdn_tc_forward_kernel<3xtf32>" : "gdn_tc_forward_kernel<tf32>");
 }
 
