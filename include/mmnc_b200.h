@@ -53,7 +53,7 @@ extern "C" {
 #define MMNC_GDN_FP32 0  /* fp32 FMA only */
 #define MMNC_GDN_TF32 1  /* tcgen05 kind::tf32, single pass (x^2 and gamma rounded to tf32) */
 #define MMNC_GDN_3XTF32 2 /* tcgen05 kind::tf32, hi/lo split in three passes (fp32-class accuracy) */
-#define MMNC_GDN_AUTO 3  /* = MMNC_GDN_3XTF32 */
+#define MMNC_GDN_AUTO 3  /* = MMNC_GDN_TF32: what the reference's own GDN (F.conv2d under cuDNN's default TF32) does on a GPU */
 
 /* ---------------------------------------------------------------------------------------------------------
  * Library state

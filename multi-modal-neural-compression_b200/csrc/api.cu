@@ -42,6 +42,11 @@ int gdn_simt_backward(const float *, const float *, int64_t, int64_t, int64_t, c
 // gdn_tc.cu
 bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision);
 int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const float *, const float *, int, int, float *, cudaStream_t);
+// gdn_tc_bwd.cu
+bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW);
+size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW);
+int gdn_tc_backward(const float *, const float *, int64_t, int64_t, int64_t, const float *, const float *, int,
+                    float *, float *, float *, void *, size_t, cudaStream_t);
 
 }  // namespace mmnc
 
@@ -61,7 +66,7 @@ extern "C" int mmnc_gdn_forward(const float *x, int64_t B, int64_t C, int64_t HW
     MMNC_REQUIRE(C <= 8192, "gdn_forward: C = %lld too large", (long long)C);
     // `precision` names the arithmetic the caller accepts.  Tensor cores are used when the shape suits the tcgen05
     // kernel in that arithmetic; everything else runs on the fp32 SIMT kernel, which is at least as accurate.
-    const int want = (precision == MMNC_GDN_AUTO) ? MMNC_GDN_3XTF32 : precision;
+    const int want = (precision == MMNC_GDN_AUTO) ? MMNC_GDN_TF32 : precision;
     if (want != MMNC_GDN_FP32 && gdn_tc_supported(B, C, HW, want))
         return gdn_tc_forward(x, B, C, HW, beta, gamma, inverse, want, y, as_stream(stream));
     return gdn_simt_forward(x, B, C, HW, beta, gamma, inverse, y, as_stream(stream));
@@ -70,7 +75,9 @@ extern "C" int mmnc_gdn_forward(const float *x, int64_t B, int64_t C, int64_t HW
 extern "C" size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int precision) {
     (void)precision;
     if (B <= 0 || C <= 0 || HW <= 0) return 256;
-    return gdn_simt_backward_workspace(B, C, HW);
+    const size_t a = gdn_simt_backward_workspace(B, C, HW), b = gdn_tc_backward_workspace(B, C, HW);
+    const bool tc = (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW);
+    return tc ? b : (a > b ? a : b);
 }
 
 extern "C" int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
@@ -88,6 +95,11 @@ extern "C" int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int6
     }
     MMNC_REQUIRE(x && g && beta && gamma && dx && workspace, "gdn_backward: null pointer");
     MMNC_REQUIRE(C <= 8192, "gdn_backward: C = %lld too large", (long long)C);
+    // single-pass TF32 on the tensor cores when the caller accepts it (auto / tf32) and the shape suits the kernel;
+    // fp32 and 3xtf32 requests, small problems and unusual channel counts run the exact fp32 SIMT kernels
+    if ((precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW))
+        return gdn_tc_backward(x, g, B, C, HW, beta, gamma, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+                               as_stream(stream));
     return gdn_simt_backward(x, g, B, C, HW, beta, gamma, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
                              as_stream(stream));
 }

@@ -168,6 +168,12 @@ gdn_reduce_kernel(const float *__restrict__ part, int ksplit, int C, float *__re
     }
 }
 
+int gdn_reduce_partials(const float *part, int ksplit, int C, float *dgamma, float *dbeta, cudaStream_t s) {
+    const int64_t n = (int64_t)C * (C + 1);
+    gdn_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, ksplit, C, dgamma, dbeta);
+    return after_launch("gdn_reduce_kernel");
+}
+
 struct SimtGrid { unsigned tiles, split; };
 static inline SimtGrid simt_grid(int64_t NP, int C) {
     const int64_t tiles = (NP + GDN_TP - 1) / GDN_TP;

@@ -1,0 +1,349 @@
+// K4 backward (tensor-core path): GDN / IGDN gradient as THREE tcgen05 contractions fused in one kernel
+// (SURVEY.md section 8 row a8, Appendix A.5).  x and the upstream gradient g are read from HBM once, dx is written
+// once — 12 B/element, the algorithmic minimum; the norm is recomputed instead of being saved by the forward.
+//
+// Per tile of 128 flattened pixels (M = 128 TMEM lanes), channels padded to P = ceil16(C + 1):
+//   MMA1  n[p][i]   = sum_j x2[p][j] gamma[i][j]        A = x^2 in TMEM,  B = gamma (smem, K-major)       -> D
+//   (epilogue 1)  rs = n^-1/2 ;  u_i = -+1/2 g_i x_i n_i^(p-1) ;  f_i = g_i n_i^p
+//   MMA2  t[p][k]   = sum_i u[p][i] gamma[i][k]         A = u in TMEM,    B = gamma^T (smem, K-major)     -> D
+//   MMA3  dG[i][j] += sum_p u[p][i] x2[p][j]            A = u^T, B = x2^T : both staged in shared memory with the
+//                                                        pixel index as K (K-major, 128-byte swizzle)     -> D3
+//   (epilogue 2)  dx_k = f_k + 2 x_k t_k
+// The padded channel C carries the constant 1 on the x^2 side, so gamma's padded column holds beta (norm comes back
+// as beta + sum) and column C of dG accumulates d beta = sum_p u.  D3 lives in TMEM for the whole kernel; every CTA
+// writes its partial (C x (C+1)) once at the end and a small kernel sums the partials in a fixed order.
+//
+// CTA = 256 threads: thread t and thread t+128 own the same pixel (TMEM lane t % 128) and split the channels
+// between them (warp w can touch TMEM lanes 32 (w % 4) .. +31, so two warpgroups can serve one tile) — the
+// per-thread register footprint is halved and twice as many loads are in flight.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mmnc {
+
+namespace tcb {
+constexpr int THREADS = 256;
+constexpr int TILE = 128;
+
+// byte offset of (row r, pixel p) in a K-major (K = pixel) 128-byte-swizzled operand whose 8-row groups are 1024 B
+// apart and whose 32-pixel K atoms are R8 * 1024 B apart
+__device__ __forceinline__ uint32_t sw128_offset(int r, int p, int R8) {
+    const int atomk = p >> 5, p32 = p & 31;
+    return (uint32_t)(((atomk * R8 + (r >> 3)) << 10) + ((r & 7) << 7) + ((((p32 >> 2) ^ (r & 7)) & 7) << 4) +
+                      ((p32 & 3) << 2));
+}
+}  // namespace tcb
+
+// KH8 = (channels per thread) / 8 = P / 16
+template <int KH8, bool kFull>
+__device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, const float *__restrict__ gb,
+                                                float *__restrict__ dxb, int64_t HW, int C, bool inverse, bool valid,
+                                                int half, int pix, uint32_t tmem_base, uint32_t lane_base,
+                                                uint8_t *ubuf, uint8_t *x2buf, int R8, uint64_t desc_b1,
+                                                uint64_t desc_b2, uint64_t desc_a3, uint64_t desc_b3,
+                                                uint32_t idesc1, uint32_t idesc2, uint32_t idesc3, uint32_t kblk2,
+                                                uint64_t *mbar, uint32_t &parity, bool first_tile) {
+    using namespace tc;
+    using namespace tcb;
+    constexpr int KH = KH8 * 8;        // channels handled by this thread
+    constexpr int P = KH * 2;          // padded channel count (K and N of the pixel-row MMAs)
+    const int c_begin = half * KH;
+    const uint32_t a_col = 0, d_col = (uint32_t)P, d3_col = (uint32_t)(2 * P);
+
+    // ---- loads: this thread's channels of x and g, all in flight
+    float xv[KH], gv[KH];
+#pragma unroll
+    for (int j = 0; j < KH; ++j) {
+        const int c = c_begin + j;
+        const int cc = (c < C) ? c : C - 1;  // padded channels re-read a real one (their weights are zero)
+        const bool ok = kFull || valid;
+        xv[j] = ok ? __ldcs(xb + (int64_t)cc * HW) : 0.f;
+        gv[j] = ok ? __ldcs(gb + (int64_t)cc * HW) : 0.f;
+    }
+    // ---- x^2 -> A (TMEM) and -> x2buf (smem, K = pixel); padded channel C is the constant 1
+#pragma unroll
+    for (int j0 = 0; j0 < KH; j0 += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c_begin + j0 + j;
+            float sq = xv[j0 + j] * xv[j0 + j];
+            if (c == C) sq = 1.f;
+            else if (c > C) sq = 0.f;
+            v[j] = to_tf32(sq);
+            if (c < 8 * R8) *reinterpret_cast<uint32_t *>(x2buf + sw128_offset(c, pix, R8)) = v[j];
+        }
+        tmem_st8(lane_base + a_col + c_begin + j0, v);
+    }
+    tmem_st_wait();
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    // ---- MMA1: D = x2 * gamma^T (+ beta through the constant column)
+    if (threadIdx.x == 0) {
+        fence_after();
+#pragma unroll
+        for (int ks = 0; ks < P / 8; ++ks)
+            mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + ks * 8, desc_b1 + (uint64_t)((ks * 256) >> 4), idesc1,
+                        ks > 0 ? 1u : 0u);
+        mma_commit(mbar);
+    }
+    mbar_wait(mbar, parity);
+    parity ^= 1;
+    fence_after();
+    // ---- epilogue 1: u -> A (TMEM) and ubuf (smem); first term of dx kept in gv
+    const float coef = inverse ? 0.5f : -0.5f;
+#pragma unroll
+    for (int j0 = 0; j0 < KH; j0 += 8) {
+        uint32_t r[8], uu[8];
+        tmem_ld8(lane_base + d_col + c_begin + j0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c_begin + j0 + j;
+            const float n = __uint_as_float(r[j]);
+            const float rs = fast_rsqrt(n);
+            const float pw = inverse ? n * rs : rs;          // n^p
+            const float pm1 = inverse ? rs : rs * rs * rs;   // n^(p-1)
+            float u = coef * gv[j0 + j] * xv[j0 + j] * pm1;
+            if (c >= C || !(kFull || valid)) u = 0.f;
+            gv[j0 + j] = gv[j0 + j] * pw;
+            uu[j] = to_tf32(u);
+            if (c < 8 * R8) *reinterpret_cast<uint32_t *>(ubuf + sw128_offset(c, pix, R8)) = uu[j];
+        }
+        tmem_st8(lane_base + a_col + c_begin + j0, uu);
+    }
+    tmem_st_wait();
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    // ---- MMA2: D = u * gamma (B = gamma^T tile);  MMA3: D3 += u^T x2 (K = 128 pixels)
+    if (threadIdx.x == 0) {
+        fence_after();
+#pragma unroll
+        for (int ks = 0; ks < P / 8; ++ks)
+            mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + ks * 8, desc_b2 + (uint64_t)((ks * kblk2) >> 4), idesc2,
+                        ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < TILE / 8; ++ks) {
+            const uint32_t off = (uint32_t)((ks >> 2) * R8 * 1024 + (ks & 3) * 32);
+            mma_tf32_ss(tmem_base + d3_col, desc_a3 + (uint64_t)(off >> 4), desc_b3 + (uint64_t)(off >> 4), idesc3,
+                        (first_tile && ks == 0) ? 0u : 1u);
+        }
+        mma_commit(mbar);
+    }
+    mbar_wait(mbar, parity);
+    parity ^= 1;
+    fence_after();
+    // ---- epilogue 2: dx = g n^p + 2 x t
+#pragma unroll
+    for (int j0 = 0; j0 < KH; j0 += 8) {
+        uint32_t r[8];
+        tmem_ld8(lane_base + d_col + c_begin + j0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c_begin + j0 + j;
+            const float out = gv[j0 + j] + 2.f * xv[j0 + j] * __uint_as_float(r[j]);
+            if ((kFull || valid) && c < C) __stcs(dxb + (int64_t)c * HW, out);
+        }
+    }
+    fence_before();
+    __syncthreads();  // A, D and both smem operands are free again
+    fence_after();
+}
+
+template <int KH8>
+__global__ void __launch_bounds__(tcb::THREADS)
+gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t NP, int64_t HW,
+                       const float *__restrict__ beta, const float *__restrict__ gamma, int inverse,
+                       float *__restrict__ dx, float *__restrict__ part, int C, uint32_t tmem_cols) {
+    using namespace tc;
+    using namespace tcb;
+    constexpr int P = KH8 * 16;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    // carve: [ubuf | x2buf] (1024-aligned swizzle atoms) then gamma
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int R8 = (C + 1 + 7) >> 3;                 // 8-row groups actually stored per K atom
+    const uint32_t buf_bytes = (uint32_t)R8 * 1024u * 4u;  // 4 K atoms of 32 pixels
+    uint8_t *ubuf = smem;
+    uint8_t *x2buf = smem + buf_bytes;
+    float *Bs = reinterpret_cast<float *>(smem + 2 * buf_bytes);                          // gamma   (N = i, K = j)
+    float *Bs2 = reinterpret_cast<float *>(smem + 2 * buf_bytes + (size_t)P * P * 4);    // gamma^T (N = k, K = i)
+    const int warp = threadIdx.x >> 5;
+    const int half = threadIdx.x >> 7;     // which half of the channels this thread owns
+    const int pix = threadIdx.x & 127;     // pixel within the tile = TMEM lane
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    // gamma tile: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]); column k = C holds beta; zero elsewhere in the padding
+    constexpr int kcores = P >> 2;
+    for (int idx = threadIdx.x; idx < P * P; idx += THREADS) {
+        const int n = idx / P, k = idx - n * P;
+        float v = 0.f;
+        if (n < C && k < C) v = gamma[(int64_t)n * C + k];
+        else if (n < C && k == C) v = beta[n];
+        else if (n >= C && k == C) v = 1.f;  // padded outputs get norm = 1 (finite)
+        const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
+        reinterpret_cast<uint32_t *>(Bs)[off] = to_tf32(v);
+        // transposed copy for MMA2 (a K-major operand again; tf32 MN-major reads of the same tile returned zeros
+        // on sm_100a, so the transpose is materialised once per CTA instead)
+        const float vt = (n < C && k < C) ? gamma[(int64_t)k * C + n] : 0.f;
+        reinterpret_cast<uint32_t *>(Bs2)[off] = to_tf32(vt);
+    }
+    // rows of the two pixel-major operands that no thread writes (r in [P', 8 R8)) must stay finite: zero them
+    for (uint32_t i = threadIdx.x; i < 2 * buf_bytes / 4; i += THREADS) reinterpret_cast<uint32_t *>(smem)[i] = 0u;
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t bs_addr = smem_u32(Bs);
+    // MMA1: B = gamma as (N = out channel, K = in channel), K-major, no swizzle
+    const uint64_t desc_b1 = make_desc(bs_addr, 128, (uint32_t)kcores * 128, 0);
+    // MMA2: B = gamma^T as (N = in channel k, K = out channel i), same layout
+    const uint64_t desc_b2 = make_desc(smem_u32(Bs2), 128, (uint32_t)kcores * 128, 0);
+    const uint32_t kblk2 = 256;
+    // MMA3: A = u^T (M = channel, K = pixel), B = x2^T (N = channel, K = pixel): K-major, 128-byte swizzle
+    const uint64_t desc_a3 = make_desc(smem_u32(ubuf), 16, 1024, 2);
+    const uint64_t desc_b3 = make_desc(smem_u32(x2buf), 16, 1024, 2);
+    const uint32_t idesc1 = make_idesc_ex(P, false, false);
+    const uint32_t idesc2 = make_idesc_ex(P, false, false);
+    const uint32_t idesc3 = make_idesc_ex(P, false, false);
+    uint32_t parity = 0;
+    bool first = true;
+
+    for (int64_t tile = blockIdx.x; tile * TILE < NP; tile += gridDim.x) {
+        const int64_t Pix = tile * TILE + pix;
+        const bool full = (tile + 1) * TILE <= NP;
+        const bool valid = Pix < NP;
+        const int64_t b = valid ? Pix / HW : 0;
+        const int64_t base = b * C * HW + (valid ? Pix - b * HW : 0);
+        if (full)
+            gdn_tc_bwd_tile<KH8, true>(x + base, g + base, dx + base, HW, C, inverse != 0, true, half, pix, tmem_base,
+                                       lane_base, ubuf, x2buf, R8, desc_b1, desc_b2, desc_a3, desc_b3, idesc1, idesc2,
+                                       idesc3, kblk2, &mbar, parity, first);
+        else
+            gdn_tc_bwd_tile<KH8, false>(x + base, g + base, dx + base, HW, C, inverse != 0, valid, half, pix, tmem_base,
+                                        lane_base, ubuf, x2buf, R8, desc_b1, desc_b2, desc_a3, desc_b3, idesc1, idesc2,
+                                        idesc3, kblk2, &mbar, parity, first);
+        first = false;
+    }
+    // ---- this CTA's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
+    float *dst = part + (int64_t)blockIdx.x * C * (C + 1);
+    if (!first && half == 0) {
+#pragma unroll 1
+        for (int j0 = 0; j0 < P; j0 += 8) {
+            uint32_t r[8];
+            tmem_ld8(lane_base + (uint32_t)(2 * P) + j0, r);
+            tmem_ld_wait();
+            if (pix < C) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j0 + j <= C) dst[(int64_t)pix * (C + 1) + j0 + j] = __uint_as_float(r[j]);
+            }
+        }
+    } else if (first && half == 0 && pix < C) {
+        for (int j = 0; j <= C; ++j) dst[(int64_t)pix * (C + 1) + j] = 0.f;  // CTA without tiles
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// fixed-order reduction of per-CTA partials [ksplit][C][C+1] -> d gamma, d beta (gdn_simt.cu)
+int gdn_reduce_partials(const float *part, int ksplit, int C, float *dgamma, float *dbeta, cudaStream_t s);
+
+static bool tcb_geometry(int64_t C, int *P, uint32_t *tmem_cols, size_t *smem) {
+    if (C < 16 || C > 128) return false;
+    *P = (int)((C + 1 + 15) / 16 * 16);
+    const int need = 3 * *P;
+    if (need > 512) return false;
+    uint32_t cols = 32;
+    while ((int)cols < need) cols <<= 1;
+    *tmem_cols = cols;
+    const size_t R8 = (size_t)(C + 1 + 7) / 8;
+    // MMA3 reads 128 rows of ubuf / P rows of x2buf: the over-read past the stored rows stays inside this allocation
+    // as long as what follows is at least as large; gamma follows and a tail pad covers the rest
+    size_t bytes = 2 * R8 * 4096 + 2 * (size_t)*P * *P * 4;
+    const size_t overread = (size_t)(3 * R8 + 16) * 1024 + R8 * 4096;  // end of the last K atom of x2buf's M=128 view
+    if (bytes < overread) bytes = overread;
+    *smem = bytes + 1024 + 256;
+    return *smem <= 227 * 1024;
+}
+
+bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW) {
+    int P;
+    uint32_t cols;
+    size_t smem;
+    return tcb_geometry(C, &P, &cols, &smem) && B * HW >= 4096;
+}
+
+static int tcb_grid(int64_t NP, uint32_t tmem_cols, size_t smem) {
+    int per_sm = 512 / (int)tmem_cols;
+    const int by_smem = (int)((227 * 1024) / smem);
+    if (per_sm > by_smem) per_sm = by_smem;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    const int64_t tiles = (NP + tcb::TILE - 1) / tcb::TILE;
+    if (grid > tiles) grid = tiles;
+    return (int)grid;
+}
+
+size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW) {
+    int P;
+    uint32_t cols;
+    size_t smem;
+    if (!tcb_geometry(C, &P, &cols, &smem)) return 0;
+    return sizeof(float) * (size_t)tcb_grid(B * HW, cols, smem) * C * (C + 1) + 256;
+}
+
+int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
+                    const float *gamma, int inverse, float *dx, float *dbeta, float *dgamma, void *workspace,
+                    size_t workspace_bytes, cudaStream_t s) {
+    int P;
+    uint32_t cols;
+    size_t smem;
+    if (!tcb_geometry(C, &P, &cols, &smem)) {
+        set_error("gdn_tc_backward: C = %lld not supported", (long long)C);
+        return MMNC_ERR_UNSUPPORTED;
+    }
+    const int64_t NP = B * HW;
+    const int grid = tcb_grid(NP, cols, smem);
+    MMNC_REQUIRE(workspace_bytes >= sizeof(float) * (size_t)grid * C * (C + 1), "gdn_backward: workspace too small");
+    // TMEM admits 512 / cols CTAs per SM: make shared memory say the same so no CTA ever spins in tcgen05.alloc
+    const int max_ctas = 512 / (int)cols;
+    const size_t min_smem = (227 * 1024) / (size_t)(max_ctas + 1) + 1;
+    if (smem < min_smem) smem = min_smem;
+    using Kernel = void (*)(const float *, const float *, int64_t, int64_t, const float *, const float *, int, float *,
+                            float *, int, uint32_t);
+    Kernel kernel = nullptr;
+    switch (P / 16) {
+        case 2: kernel = gdn_tc_backward_kernel<2>; break;
+        case 3: kernel = gdn_tc_backward_kernel<3>; break;
+        case 4: kernel = gdn_tc_backward_kernel<4>; break;
+        case 5: kernel = gdn_tc_backward_kernel<5>; break;
+        case 6: kernel = gdn_tc_backward_kernel<6>; break;
+        case 7: kernel = gdn_tc_backward_kernel<7>; break;
+        case 8: kernel = gdn_tc_backward_kernel<8>; break;
+        case 9: kernel = gdn_tc_backward_kernel<9>; break;
+        default: break;
+    }
+    if (kernel == nullptr) {
+        set_error("gdn_tc_backward: no kernel instance for C = %lld", (long long)C);
+        return MMNC_ERR_UNSUPPORTED;
+    }
+    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float *part = static_cast<float *>(workspace);
+    kernel<<<(unsigned)grid, tcb::THREADS, smem, s>>>(x, g, NP, HW, beta, gamma, inverse, dx, part, (int)C, cols);
+    if (int rc = after_launch("gdn_tc_backward_kernel")) return rc;
+    return gdn_reduce_partials(part, grid, (int)C, dgamma, dbeta, s);
+}
+
+}  // namespace mmnc

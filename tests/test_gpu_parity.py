@@ -327,6 +327,36 @@ def test_gdn_backward_fp32(shape, inverse):
     assert torch.allclose(ours.gamma.grad.cpu().double(), refd.gamma.grad, rtol=1e-3, atol=1e-4)
 
 
+@pytest.mark.parametrize("shape", [(2, 50, 64, 64), (1, 100, 64, 64), (3, 16, 48, 40), (4, 128, 32, 32), (2, 33, 50, 50),
+                                   (1, 64, 64, 65), (2, 24, 37, 59), (2, 120, 48, 48)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_backward_tensor_core(shape, inverse):
+    """Fused tcgen05 backward (three single-pass TF32 contractions).  Stated tolerance: TF32 rounds x^2, u and gamma
+    to 10-bit mantissas -> 2e-3 relative (of the largest entry) on dx; d gamma / d beta are sums over all pixels
+    of tf32-rounded products, held to 2e-3 of their largest entry."""
+    torch.manual_seed(16)
+    C = shape[1]
+    ours, ref = _pair_gdn(C, inverse, precision="tf32")
+    refd = R.GDN(C, inverse=inverse).double()
+    refd.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
+    x, g = torch.randn(*shape), torch.randn(*shape)
+    xd = x.to(DEV).requires_grad_(True)
+    before = mm.launch_count()
+    (ours(xd) * g.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    if C <= 112:  # larger C: gamma and gamma^T no longer fit shared memory next to the pixel-major operands -> SIMT
+        assert mm.launch_count() - before == 3 + 2 + 2, "fwd: 2 reparam + 1; bwd: fused kernel + reduce; 2 reparam bwd"
+    x64 = x.double().requires_grad_(True)
+    (refd(x64) * g.double()).sum().backward()
+
+    def close(a, b, tol):
+        return ((a.cpu().double() - b).abs().max() / b.abs().max()).item() <= tol
+
+    assert close(xd.grad, x64.grad, 2e-3), ((xd.grad.cpu().double() - x64.grad).abs().max(), x64.grad.abs().max())
+    assert close(ours.beta.grad, refd.beta.grad, 2e-3)
+    assert close(ours.gamma.grad, refd.gamma.grad, 2e-3)
+
+
 def test_gdn_reparam_lower_bound_gradient():
     """A.2 / A.5: below the bound the gradient passes only if it is negative."""
     C = 4
