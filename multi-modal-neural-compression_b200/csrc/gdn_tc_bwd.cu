@@ -36,31 +36,52 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int p, int R8) {
 }
 }  // namespace tcb
 
-// KH8 = (channels per thread) / 8 = P / 16
-template <int KH8, bool kFull>
-__device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, const float *__restrict__ gb,
-                                                float *__restrict__ dxb, int64_t HW, int C, bool inverse, bool valid,
-                                                int half, int pix, uint32_t tmem_base, uint32_t lane_base,
-                                                uint8_t *ubuf, uint8_t *x2buf, int R8, uint64_t desc_b1,
-                                                uint64_t desc_b2, uint64_t desc_a3, uint64_t desc_b3,
-                                                uint32_t idesc1, uint32_t idesc2, uint32_t idesc3, uint32_t kblk2,
-                                                uint64_t *mbar, uint32_t &parity, bool first_tile) {
+// KH8 = (channels per thread) / 8 = P / 16.  HALF (which half of the channels), kInverse and kFull are template
+// parameters so that every channel index below is a compile-time constant: only the last 16 padded channels of
+// HALF 1 keep run-time checks against C, everything else is straight-line code with immediate offsets.
+struct TileCtx {
+    int HW, C, pix, R8;
+    uint32_t tmem_base, lane_base, idesc;
+    uint8_t *ubuf, *x2buf;
+    uint64_t desc_b1, desc_b2, desc_a3, desc_b3;
+    uint64_t *mbar;
+};
+
+template <int KH8, int HALF, bool kInverse, bool kFull>
+__device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ xb, const float *__restrict__ gb,
+                                                float *__restrict__ dxb, int HW, int C, bool valid, int pix,
+                                                uint32_t tmem_base, uint32_t lane_base, uint8_t *ubuf,
+                                                uint8_t *x2buf, int R8, uint64_t desc_b1, uint64_t desc_b2,
+                                                uint64_t desc_a3, uint64_t desc_b3, uint32_t idesc, uint64_t *mbar,
+                                                uint32_t &parity, bool first_tile) {
     using namespace tc;
     using namespace tcb;
     constexpr int KH = KH8 * 8;        // channels handled by this thread
     constexpr int P = KH * 2;          // padded channel count (K and N of the pixel-row MMAs)
-    const int c_begin = half * KH;
-    const uint32_t a_col = 0, d_col = (uint32_t)P, d3_col = (uint32_t)(2 * P);
+    constexpr int c_begin = HALF * KH;
+    constexpr int SAFE = P - 16;       // channels below this are always real (C > P - 16)
+    constexpr uint32_t a_col = 0, d_col = (uint32_t)P, d3_col = (uint32_t)(2 * P);
+    const bool ok = kFull || valid;
+    // swizzled shared-memory offsets: row c = c_begin + j0 + j with j0, c_begin multiples of 8, so (c & 7) == j and
+    // (c >> 3) is a constant: one register per j holds the thread-dependent part, the row group is an immediate
+    uint32_t soff[8];
+    {
+        const int atomk = pix >> 5, p32 = pix & 31;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            soff[j] = (uint32_t)(((atomk * R8 + (c_begin >> 3)) << 10) + (j << 7) + ((((p32 >> 2) ^ j) & 7) << 4) +
+                                 ((p32 & 3) << 2));
+    }
+    const int rows = 8 * R8;  // rows that exist in ubuf / x2buf
 
-    // ---- loads: this thread's channels of x and g, all in flight
+    // ---- loads: this thread's channels of x and g, all in flight (32-bit element offsets from a per-pixel base)
     float xv[KH], gv[KH];
 #pragma unroll
     for (int j = 0; j < KH; ++j) {
         const int c = c_begin + j;
-        const int cc = (c < C) ? c : C - 1;  // padded channels re-read a real one (their weights are zero)
-        const bool ok = kFull || valid;
-        xv[j] = ok ? __ldcs(xb + (int64_t)cc * HW) : 0.f;
-        gv[j] = ok ? __ldcs(gb + (int64_t)cc * HW) : 0.f;
+        const int cc = (c < SAFE) ? c : ((c < C) ? c : C - 1);  // padded channels re-read a real one (weights are 0)
+        xv[j] = ok ? __ldcs(xb + cc * HW) : 0.f;
+        gv[j] = ok ? __ldcs(gb + cc * HW) : 0.f;
     }
     // ---- x^2 -> A (TMEM) and -> x2buf (smem, K = pixel); padded channel C is the constant 1
 #pragma unroll
@@ -70,10 +91,9 @@ __device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, co
         for (int j = 0; j < 8; ++j) {
             const int c = c_begin + j0 + j;
             float sq = xv[j0 + j] * xv[j0 + j];
-            if (c == C) sq = 1.f;
-            else if (c > C) sq = 0.f;
+            if (c >= SAFE) sq = (c < C) ? sq : ((c == C) ? 1.f : 0.f);
             v[j] = to_tf32(sq);
-            if (c < 8 * R8) *reinterpret_cast<uint32_t *>(x2buf + sw128_offset(c, pix, R8)) = v[j];
+            if (c < SAFE || c < rows) *reinterpret_cast<uint32_t *>(x2buf + soff[j] + (j0 << 7)) = v[j];
         }
         tmem_st8(lane_base + a_col + c_begin + j0, v);
     }
@@ -86,7 +106,7 @@ __device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, co
         fence_after();
 #pragma unroll
         for (int ks = 0; ks < P / 8; ++ks)
-            mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + ks * 8, desc_b1 + (uint64_t)((ks * 256) >> 4), idesc1,
+            mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + ks * 8, desc_b1 + (uint64_t)((ks * 256) >> 4), idesc,
                         ks > 0 ? 1u : 0u);
         mma_commit(mbar);
     }
@@ -94,7 +114,7 @@ __device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, co
     parity ^= 1;
     fence_after();
     // ---- epilogue 1: u -> A (TMEM) and ubuf (smem); first term of dx kept in gv
-    const float coef = inverse ? 0.5f : -0.5f;
+    constexpr float coef = kInverse ? 0.5f : -0.5f;
 #pragma unroll
     for (int j0 = 0; j0 < KH; j0 += 8) {
         uint32_t r[8], uu[8];
@@ -105,13 +125,14 @@ __device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, co
             const int c = c_begin + j0 + j;
             const float n = __uint_as_float(r[j]);
             const float rs = fast_rsqrt(n);
-            const float pw = inverse ? n * rs : rs;          // n^p
-            const float pm1 = inverse ? rs : rs * rs * rs;   // n^(p-1)
-            float u = coef * gv[j0 + j] * xv[j0 + j] * pm1;
-            if (c >= C || !(kFull || valid)) u = 0.f;
+            const float pw = kInverse ? n * rs : rs;            // n^p
+            const float pm1 = kInverse ? rs : rs * rs * rs;     // n^(p-1)
+            float u = (coef * gv[j0 + j]) * (xv[j0 + j] * pm1);
+            if (c >= SAFE && c >= C) u = 0.f;
+            if (!kFull && !valid) u = 0.f;
             gv[j0 + j] = gv[j0 + j] * pw;
             uu[j] = to_tf32(u);
-            if (c < 8 * R8) *reinterpret_cast<uint32_t *>(ubuf + sw128_offset(c, pix, R8)) = uu[j];
+            if (c < SAFE || c < rows) *reinterpret_cast<uint32_t *>(ubuf + soff[j] + (j0 << 7)) = uu[j];
         }
         tmem_st8(lane_base + a_col + c_begin + j0, uu);
     }
@@ -124,12 +145,12 @@ __device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, co
         fence_after();
 #pragma unroll
         for (int ks = 0; ks < P / 8; ++ks)
-            mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + ks * 8, desc_b2 + (uint64_t)((ks * kblk2) >> 4), idesc2,
+            mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + ks * 8, desc_b2 + (uint64_t)((ks * 256) >> 4), idesc,
                         ks > 0 ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < TILE / 8; ++ks) {
             const uint32_t off = (uint32_t)((ks >> 2) * R8 * 1024 + (ks & 3) * 32);
-            mma_tf32_ss(tmem_base + d3_col, desc_a3 + (uint64_t)(off >> 4), desc_b3 + (uint64_t)(off >> 4), idesc3,
+            mma_tf32_ss(tmem_base + d3_col, desc_a3 + (uint64_t)(off >> 4), desc_b3 + (uint64_t)(off >> 4), idesc,
                         (first_tile && ks == 0) ? 0u : 1u);
         }
         mma_commit(mbar);
@@ -146,8 +167,8 @@ __device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, co
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = c_begin + j0 + j;
-            const float out = gv[j0 + j] + 2.f * xv[j0 + j] * __uint_as_float(r[j]);
-            if ((kFull || valid) && c < C) __stcs(dxb + (int64_t)c * HW, out);
+            const float out = fmaf(2.f * xv[j0 + j], __uint_as_float(r[j]), gv[j0 + j]);
+            if (ok && (c < SAFE || c < C)) __stcs(dxb + c * HW, out);
         }
     }
     fence_before();
@@ -155,10 +176,43 @@ __device__ __forceinline__ void gdn_tc_bwd_tile(const float *__restrict__ xb, co
     fence_after();
 }
 
-template <int KH8>
+// the rare partial tile (last tile of the tensor) takes the predicated body out of line so that it does not
+// weigh on the register allocation of the steady-state loop
+template <int KH8, int HALF, bool kInverse>
+__device__ __noinline__ void gdn_tc_bwd_tile_partial(const float *xb, const float *gb, float *dxb, bool valid,
+                                                     const TileCtx &t, uint32_t &parity, bool first) {
+    gdn_tc_bwd_tile_body<KH8, HALF, kInverse, false>(xb, gb, dxb, t.HW, t.C, valid, t.pix, t.tmem_base, t.lane_base,
+                                                     t.ubuf, t.x2buf, t.R8, t.desc_b1, t.desc_b2, t.desc_a3, t.desc_b3,
+                                                     t.idesc, t.mbar, parity, first);
+}
+
+template <int KH8, int HALF, bool kInverse>
+__device__ __forceinline__ bool gdn_tc_bwd_loop(const float *__restrict__ x, const float *__restrict__ g,
+                                                float *__restrict__ dx, int64_t NP, int64_t HW, const TileCtx &t) {
+    using namespace tcb;
+    uint32_t parity = 0;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile * TILE < NP; tile += gridDim.x) {
+        const int64_t Pix = tile * TILE + t.pix;
+        const bool valid = Pix < NP;
+        const int64_t b = valid ? Pix / HW : 0;
+        const int64_t base = b * t.C * HW + (valid ? Pix - b * HW : 0);
+        if ((tile + 1) * TILE <= NP)
+            gdn_tc_bwd_tile_body<KH8, HALF, kInverse, true>(x + base, g + base, dx + base, t.HW, t.C, true, t.pix,
+                                                            t.tmem_base, t.lane_base, t.ubuf, t.x2buf, t.R8, t.desc_b1,
+                                                            t.desc_b2, t.desc_a3, t.desc_b3, t.idesc, t.mbar, parity,
+                                                            first);
+        else
+            gdn_tc_bwd_tile_partial<KH8, HALF, kInverse>(x + base, g + base, dx + base, valid, t, parity, first);
+        first = false;
+    }
+    return first;
+}
+
+template <int KH8, bool kInverse>
 __global__ void __launch_bounds__(tcb::THREADS)
 gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t NP, int64_t HW,
-                       const float *__restrict__ beta, const float *__restrict__ gamma, int inverse,
+                       const float *__restrict__ beta, const float *__restrict__ gamma,
                        float *__restrict__ dx, float *__restrict__ part, int C, uint32_t tmem_cols) {
     using namespace tc;
     using namespace tcb;
@@ -208,32 +262,20 @@ gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g,
     const uint64_t desc_b1 = make_desc(bs_addr, 128, (uint32_t)kcores * 128, 0);
     // MMA2: B = gamma^T as (N = in channel k, K = out channel i), same layout
     const uint64_t desc_b2 = make_desc(smem_u32(Bs2), 128, (uint32_t)kcores * 128, 0);
-    const uint32_t kblk2 = 256;
     // MMA3: A = u^T (M = channel, K = pixel), B = x2^T (N = channel, K = pixel): K-major, 128-byte swizzle
     const uint64_t desc_a3 = make_desc(smem_u32(ubuf), 16, 1024, 2);
     const uint64_t desc_b3 = make_desc(smem_u32(x2buf), 16, 1024, 2);
-    const uint32_t idesc1 = make_idesc_ex(P, false, false);
-    const uint32_t idesc2 = make_idesc_ex(P, false, false);
-    const uint32_t idesc3 = make_idesc_ex(P, false, false);
-    uint32_t parity = 0;
-    bool first = true;
-
-    for (int64_t tile = blockIdx.x; tile * TILE < NP; tile += gridDim.x) {
-        const int64_t Pix = tile * TILE + pix;
-        const bool full = (tile + 1) * TILE <= NP;
-        const bool valid = Pix < NP;
-        const int64_t b = valid ? Pix / HW : 0;
-        const int64_t base = b * C * HW + (valid ? Pix - b * HW : 0);
-        if (full)
-            gdn_tc_bwd_tile<KH8, true>(x + base, g + base, dx + base, HW, C, inverse != 0, true, half, pix, tmem_base,
-                                       lane_base, ubuf, x2buf, R8, desc_b1, desc_b2, desc_a3, desc_b3, idesc1, idesc2,
-                                       idesc3, kblk2, &mbar, parity, first);
-        else
-            gdn_tc_bwd_tile<KH8, false>(x + base, g + base, dx + base, HW, C, inverse != 0, valid, half, pix, tmem_base,
-                                        lane_base, ubuf, x2buf, R8, desc_b1, desc_b2, desc_a3, desc_b3, idesc1, idesc2,
-                                        idesc3, kblk2, &mbar, parity, first);
-        first = false;
-    }
+    const uint32_t idesc = make_idesc_ex(P, false, false);
+    TileCtx ctx;
+    ctx.HW = (int)HW;  // channel stride in elements (< 2^31; per-pixel bases stay 64-bit)
+    ctx.C = C; ctx.pix = pix; ctx.R8 = R8;
+    ctx.tmem_base = tmem_base; ctx.lane_base = lane_base; ctx.idesc = idesc;
+    ctx.ubuf = ubuf; ctx.x2buf = x2buf;
+    ctx.desc_b1 = desc_b1; ctx.desc_b2 = desc_b2; ctx.desc_a3 = desc_a3; ctx.desc_b3 = desc_b3;
+    ctx.mbar = &mbar;
+    // the two warpgroups run the same tile sequence in lock step, each on its half of the channels
+    const bool first = (half == 0) ? gdn_tc_bwd_loop<KH8, 0, kInverse>(x, g, dx, NP, HW, ctx)
+                                   : gdn_tc_bwd_loop<KH8, 1, kInverse>(x, g, dx, NP, HW, ctx);
     // ---- this CTA's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
     float *dst = part + (int64_t)blockIdx.x * C * (C + 1);
     if (!first && half == 0) {
@@ -260,7 +302,7 @@ gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g,
 int gdn_reduce_partials(const float *part, int ksplit, int C, float *dgamma, float *dbeta, cudaStream_t s);
 
 static bool tcb_geometry(int64_t C, int *P, uint32_t *tmem_cols, size_t *smem) {
-    if (C < 16 || C > 128) return false;
+    if (C < 16 || C > 111) return false;
     *P = (int)((C + 1 + 15) / 16 * 16);
     const int need = 3 * *P;
     if (need > 512) return false;
@@ -281,7 +323,7 @@ bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW) {
     int P;
     uint32_t cols;
     size_t smem;
-    return tcb_geometry(C, &P, &cols, &smem) && B * HW >= 4096;
+    return tcb_geometry(C, &P, &cols, &smem) && B * HW >= 4096 && HW < (1 << 24);
 }
 
 static int tcb_grid(int64_t NP, uint32_t tmem_cols, size_t smem) {
@@ -321,27 +363,22 @@ int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_
     const int max_ctas = 512 / (int)cols;
     const size_t min_smem = (227 * 1024) / (size_t)(max_ctas + 1) + 1;
     if (smem < min_smem) smem = min_smem;
-    using Kernel = void (*)(const float *, const float *, int64_t, int64_t, const float *, const float *, int, float *,
+    using Kernel = void (*)(const float *, const float *, int64_t, int64_t, const float *, const float *, float *,
                             float *, int, uint32_t);
     Kernel kernel = nullptr;
+#define MMNC_CASE(N) case N: kernel = inverse ? (Kernel)gdn_tc_backward_kernel<N, true> : (Kernel)gdn_tc_backward_kernel<N, false>; break;
     switch (P / 16) {
-        case 2: kernel = gdn_tc_backward_kernel<2>; break;
-        case 3: kernel = gdn_tc_backward_kernel<3>; break;
-        case 4: kernel = gdn_tc_backward_kernel<4>; break;
-        case 5: kernel = gdn_tc_backward_kernel<5>; break;
-        case 6: kernel = gdn_tc_backward_kernel<6>; break;
-        case 7: kernel = gdn_tc_backward_kernel<7>; break;
-        case 8: kernel = gdn_tc_backward_kernel<8>; break;
-        case 9: kernel = gdn_tc_backward_kernel<9>; break;
+        MMNC_CASE(2) MMNC_CASE(3) MMNC_CASE(4) MMNC_CASE(5) MMNC_CASE(6) MMNC_CASE(7)
         default: break;
     }
+#undef MMNC_CASE
     if (kernel == nullptr) {
         set_error("gdn_tc_backward: no kernel instance for C = %lld", (long long)C);
         return MMNC_ERR_UNSUPPORTED;
     }
     MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float *part = static_cast<float *>(workspace);
-    kernel<<<(unsigned)grid, tcb::THREADS, smem, s>>>(x, g, NP, HW, beta, gamma, inverse, dx, part, (int)C, cols);
+    kernel<<<(unsigned)grid, tcb::THREADS, smem, s>>>(x, g, NP, HW, beta, gamma, dx, part, (int)C, cols);
     if (int rc = after_launch("gdn_tc_backward_kernel")) return rc;
     return gdn_reduce_partials(part, grid, (int)C, dgamma, dbeta, s);
 }
