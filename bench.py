@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rans", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the rate-path step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--precision", default="auto", help="GDN contraction: auto | fp32 | tf32 | 3xtf32")
     return ap.parse_args()
 
@@ -140,6 +141,7 @@ class RatePathHarness:
             mod.beta.grad.copy_(gb)
             mod.gamma.grad.copy_(gg)
         self.eb.train(), self.gc.train()
+        mm.ops.noise_source.step()            # advance the device-side Philox stream (part of the captured graph)
         z_hat, z_lik = self.eb(self.z)        # K1 + K2
         y_hat, y_lik = self.gc(self.y, self.scales)  # K1 + K3
         lik = mm.compressors.LikelihoodDict(y=y_lik, z=z_lik)
@@ -398,8 +400,27 @@ def run_b200(args):
 
     # -------- value: the hot path with inputs resident in HBM
     harness = RatePathHarness(mm, model, B, device, torch)
+    mm.ops.noise_source.enable_device_state(device, seed=21)  # Philox (seed, offset) on the device: graph-safe
+    run_step = lambda: harness.step(dist, world)  # noqa: E731
+    graph = None
+    if not args.no_graph:
+        # The step is ~600 small launches: without a graph the host cannot issue them as fast as the GPU retires
+        # them.  Capture once, replay per step (fresh noise each replay through the device-side Philox state).
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                harness.step(dist, world)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        launches_per_step0 = mm.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            harness.step(dist, world)
+        launches_per_step = mm.launch_count() - launches_per_step0
+        run_step = graph.replay
     for _ in range(max(args.warmup, 3)):
-        harness.step(dist, world)
+        run_step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -408,11 +429,13 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        harness.step(dist, world)
+        run_step()
     e1.record()
     barrier()
     t_rate = max_over_ranks(e0.elapsed_time(e1) * 1e-3) / args.steps
-    launches = mm.launch_count() - launches0
+    launches = (launches_per_step * args.steps) if graph is not None else (mm.launch_count() - launches0)
+    mm.ops.noise_source.disable_device_state()
+    del graph
     value = world * B / t_rate
 
     # -------- e2e: public API, host batch, H2D + D2H inside the timed region
@@ -472,6 +495,7 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "images_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"dp{world}", "gdn_precision": args.precision,
                        "gdn_elements_per_image": harness.gdn_elems_per_image,
+                       "launch": "eager" if args.no_graph else "CUDA graph replay of one captured step",
                        "l2_policy": "inputs larger than L2 (4.7 GB of GDN activations per step vs 126 MB L2)"},
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
         }

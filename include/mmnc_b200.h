@@ -43,6 +43,9 @@ extern "C" {
 #define MMNC_QUANT_NOISE_PHILOX 1 /* train: x + U(-1/2,1/2) from Philox4x32-10(seed, element index + offset) */
 #define MMNC_QUANT_NOISE_GIVEN 2  /* train (test hook): x + noise[i] read from memory */
 #define MMNC_QUANT_IDENTITY 3     /* input is already quantised: v = x */
+#define MMNC_QUANT_NOISE_PHILOX_DEV 4 /* like PHILOX, but `noise` points at two device uint64 {seed, offset}: the
+                                        stream can be advanced by a kernel, so a captured CUDA graph draws fresh
+                                        noise on every replay */
 
 /* likelihood_form for the EntropyBottleneck (SURVEY.md A.3 version switch) */
 #define MMNC_EB_FORM_SIGN 0  /* CompressAI 1.2.x: |sigmoid(s*up) - sigmoid(s*lo)|, s = -sign(lo+up) */
@@ -167,6 +170,17 @@ size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int p
 int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
                       const float *gamma, int inverse, int precision, float *dx, float *dbeta, float *dgamma,
                       void *workspace, size_t workspace_bytes, void *stream);
+/* Same two calls taking the RAW parameters of compressai.layers.GDN (`beta`, `gamma` as stored in the state dict):
+ * the NonNegativeParametrizer re-parametrisation (effective = max(p, bound)^2 - pedestal) is applied while the
+ * kernels stage the parameters, and the gradients come back w.r.t. the raw parameters with LowerBound's custom
+ * gradient applied — one launch forward, two backward, instead of 3 + 5. */
+int mmnc_gdn_forward_raw(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
+                         const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal, int inverse,
+                         int precision, float *y, void *stream);
+int mmnc_gdn_backward_raw(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
+                          const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal, int inverse,
+                          int precision, float *dx, float *dbeta_raw, float *dgamma_raw, void *workspace,
+                          size_t workspace_bytes, void *stream);
 /* NonNegativeParametrizer.forward: out = max(p, bound)^2 - pedestal, and its backward with LowerBound's
  * custom gradient (pass when p >= bound or when the incoming gradient is negative). */
 int mmnc_nonneg_reparam_forward(const float *p, int64_t n, float bound, float pedestal, float *out, void *stream);

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "gdn_params.cuh"
 
 namespace mmnc {
 
@@ -35,18 +36,24 @@ int sm_count() {
 }
 
 // gdn_simt.cu
-int gdn_simt_forward(const float *, int64_t, int64_t, int64_t, const float *, const float *, int, float *, cudaStream_t);
+int gdn_simt_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, cudaStream_t);
 size_t gdn_simt_backward_workspace(int64_t, int64_t, int64_t);
-int gdn_simt_backward(const float *, const float *, int64_t, int64_t, int64_t, const float *, const float *, int,
-                      float *, float *, float *, void *, size_t, cudaStream_t);
+int gdn_simt_backward(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
+                      float *, void *, size_t, cudaStream_t);
+// gdn_small.cu
+bool gdn_small_supported(int64_t C);
+size_t gdn_small_backward_workspace(int64_t B, int64_t C, int64_t HW);
+int gdn_small_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, cudaStream_t);
+int gdn_small_backward(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
+                       float *, void *, size_t, cudaStream_t);
 // gdn_tc.cu
 bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision);
-int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const float *, const float *, int, int, float *, cudaStream_t);
+int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, int, float *, cudaStream_t);
 // gdn_tc_bwd.cu
 bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW);
 size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW);
-int gdn_tc_backward(const float *, const float *, int64_t, int64_t, int64_t, const float *, const float *, int,
-                    float *, float *, float *, void *, size_t, cudaStream_t);
+int gdn_tc_backward(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
+                    float *, void *, size_t, cudaStream_t);
 
 }  // namespace mmnc
 
@@ -57,32 +64,52 @@ extern "C" const char *mmnc_last_error(void) { return g_error; }
 extern "C" uint64_t mmnc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int mmnc_device_sm_count(void) { return sm_count(); }
 
-extern "C" int mmnc_gdn_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta,
-                                const float *gamma, int inverse, int precision, float *y, void *stream) {
+static int gdn_forward_impl(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse,
+                            int precision, float *y, void *stream) {
     MMNC_REQUIRE(B >= 0 && C >= 0 && HW >= 0, "gdn_forward: negative dimension");
     MMNC_REQUIRE(precision >= 0 && precision <= 3, "gdn_forward: bad precision %d", precision);
     if (B * C * HW == 0) return MMNC_OK;
-    MMNC_REQUIRE(x && beta && gamma && y, "gdn_forward: null pointer");
+    MMNC_REQUIRE(x && prm.beta && prm.gamma && y, "gdn_forward: null pointer");
     MMNC_REQUIRE(C <= 8192, "gdn_forward: C = %lld too large", (long long)C);
     // `precision` names the arithmetic the caller accepts.  Tensor cores are used when the shape suits the tcgen05
     // kernel in that arithmetic; everything else runs on the fp32 SIMT kernel, which is at least as accurate.
+    if (gdn_small_supported(C)) return gdn_small_forward(x, B, C, HW, prm, inverse, y, as_stream(stream));  // fp32
     const int want = (precision == MMNC_GDN_AUTO) ? MMNC_GDN_TF32 : precision;
     if (want != MMNC_GDN_FP32 && gdn_tc_supported(B, C, HW, want))
-        return gdn_tc_forward(x, B, C, HW, beta, gamma, inverse, want, y, as_stream(stream));
-    return gdn_simt_forward(x, B, C, HW, beta, gamma, inverse, y, as_stream(stream));
+        return gdn_tc_forward(x, B, C, HW, prm, inverse, want, y, as_stream(stream));
+    return gdn_simt_forward(x, B, C, HW, prm, inverse, y, as_stream(stream));
+}
+
+static GdnParams gdn_raw(const float *beta, const float *gamma, float bb, float gb, float ped) {
+    GdnParams p;
+    p.beta = beta; p.gamma = gamma; p.beta_bound = bb; p.gamma_bound = gb; p.pedestal = ped; p.raw = 1;
+    return p;
+}
+
+extern "C" int mmnc_gdn_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta,
+                                const float *gamma, int inverse, int precision, float *y, void *stream) {
+    return gdn_forward_impl(x, B, C, HW, gdn_effective(beta, gamma), inverse, precision, y, stream);
+}
+
+extern "C" int mmnc_gdn_forward_raw(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
+                                    const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal,
+                                    int inverse, int precision, float *y, void *stream) {
+    return gdn_forward_impl(x, B, C, HW, gdn_raw(beta_raw, gamma_raw, beta_bound, gamma_bound, pedestal), inverse,
+                            precision, y, stream);
 }
 
 extern "C" size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int precision) {
     (void)precision;
     if (B <= 0 || C <= 0 || HW <= 0) return 256;
+    if (gdn_small_supported(C)) return gdn_small_backward_workspace(B, C, HW);
     const size_t a = gdn_simt_backward_workspace(B, C, HW), b = gdn_tc_backward_workspace(B, C, HW);
     const bool tc = (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW);
     return tc ? b : (a > b ? a : b);
 }
 
-extern "C" int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
-                                 const float *gamma, int inverse, int precision, float *dx, float *dbeta,
-                                 float *dgamma, void *workspace, size_t workspace_bytes, void *stream) {
+static int gdn_backward_impl(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
+                             int inverse, int precision, float *dx, float *dbeta, float *dgamma, void *workspace,
+                             size_t workspace_bytes, void *stream) {
     MMNC_REQUIRE(B >= 0 && C >= 0 && HW >= 0, "gdn_backward: negative dimension");
     MMNC_REQUIRE(precision >= 0 && precision <= 3, "gdn_backward: bad precision %d", precision);
     MMNC_REQUIRE(dbeta && dgamma, "gdn_backward: null pointer");
@@ -93,13 +120,32 @@ extern "C" int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int6
         }
         return MMNC_OK;
     }
-    MMNC_REQUIRE(x && g && beta && gamma && dx && workspace, "gdn_backward: null pointer");
+    MMNC_REQUIRE(x && g && prm.beta && prm.gamma && dx && workspace, "gdn_backward: null pointer");
     MMNC_REQUIRE(C <= 8192, "gdn_backward: C = %lld too large", (long long)C);
     // single-pass TF32 on the tensor cores when the caller accepts it (auto / tf32) and the shape suits the kernel;
     // fp32 and 3xtf32 requests, small problems and unusual channel counts run the exact fp32 SIMT kernels
+    if (gdn_small_supported(C))
+        return gdn_small_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+                                  as_stream(stream));
     if ((precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW))
-        return gdn_tc_backward(x, g, B, C, HW, beta, gamma, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+        return gdn_tc_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
                                as_stream(stream));
-    return gdn_simt_backward(x, g, B, C, HW, beta, gamma, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+    return gdn_simt_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
                              as_stream(stream));
+}
+
+extern "C" int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
+                                 const float *gamma, int inverse, int precision, float *dx, float *dbeta,
+                                 float *dgamma, void *workspace, size_t workspace_bytes, void *stream) {
+    return gdn_backward_impl(x, g, B, C, HW, gdn_effective(beta, gamma), inverse, precision, dx, dbeta, dgamma,
+                             workspace, workspace_bytes, stream);
+}
+
+extern "C" int mmnc_gdn_backward_raw(const float *x, const float *g, int64_t B, int64_t C, int64_t HW,
+                                     const float *beta_raw, const float *gamma_raw, float beta_bound,
+                                     float gamma_bound, float pedestal, int inverse, int precision, float *dx,
+                                     float *dbeta_raw, float *dgamma_raw, void *workspace, size_t workspace_bytes,
+                                     void *stream) {
+    return gdn_backward_impl(x, g, B, C, HW, gdn_raw(beta_raw, gamma_raw, beta_bound, gamma_bound, pedestal), inverse,
+                             precision, dx, dbeta_raw, dgamma_raw, workspace, workspace_bytes, stream);
 }

@@ -34,6 +34,12 @@ eb_forward_kernel(const float *__restrict__ x, int64_t B, int64_t C, int64_t S, 
     const float med = medians[c];
     const int64_t n = B * S;
     float acc = 0.f;
+    if (noise_mode == MMNC_QUANT_NOISE_PHILOX_DEV) {  // (seed, offset) live in device memory: CUDA-graph friendly
+        const uint64_t *st = reinterpret_cast<const uint64_t *>(noise);
+        seed = st[0];
+        offset += st[1];
+        noise_mode = MMNC_QUANT_NOISE_PHILOX;
+    }
     for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
         const int64_t a = eb_addr(e, c, C, S);
         const float xv = x[a];
@@ -168,11 +174,12 @@ extern "C" int mmnc_eb_forward(const float *x, int64_t B, int64_t C, int64_t S, 
                                uint64_t offset, float likelihood_bound, int likelihood_form, float *out,
                                float *lik, float *lnsum, void *stream) {
     MMNC_REQUIRE(B >= 0 && C >= 0 && S >= 0, "eb_forward: negative dimension");
-    MMNC_REQUIRE(noise_mode >= 0 && noise_mode <= 3, "eb_forward: bad noise_mode %d", noise_mode);
+    MMNC_REQUIRE(noise_mode >= 0 && noise_mode <= 4, "eb_forward: bad noise_mode %d", noise_mode);
     MMNC_REQUIRE(likelihood_form == 0 || likelihood_form == 1, "eb_forward: bad likelihood_form");
     if (B * C * S == 0) return MMNC_OK;
     MMNC_REQUIRE(x && params && medians && out && lik, "eb_forward: null pointer");
-    MMNC_REQUIRE(noise_mode != MMNC_QUANT_NOISE_GIVEN || noise, "eb_forward: noise_mode GIVEN needs noise");
+    MMNC_REQUIRE((noise_mode != MMNC_QUANT_NOISE_GIVEN && noise_mode != MMNC_QUANT_NOISE_PHILOX_DEV) || noise,
+                 "eb_forward: this noise_mode needs the noise pointer");
     MMNC_REQUIRE(C <= 2147483647LL, "eb_forward: too many channels");
     dim3 grid((unsigned)C, (unsigned)eb_splits(C, B * S));
     eb_forward_kernel<<<grid, EB_THREADS, 0, as_stream(stream)>>>(x, B, C, S, params, medians, noise_mode, noise,

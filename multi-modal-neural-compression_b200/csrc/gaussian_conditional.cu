@@ -26,6 +26,12 @@ gc_forward_kernel(const float *__restrict__ y, const float *__restrict__ scales,
     const int64_t n = B * Ss;
     const bool bcast = (Sy != Ss);
     float acc = 0.f;
+    if (noise_mode == MMNC_QUANT_NOISE_PHILOX_DEV) {  // (seed, offset) live in device memory: CUDA-graph friendly
+        const uint64_t *st = reinterpret_cast<const uint64_t *>(noise);
+        seed = st[0];
+        offset += st[1];
+        noise_mode = MMNC_QUANT_NOISE_PHILOX;
+    }
     for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
         const int64_t b = e / Ss, s = e - b * Ss;
         const int64_t ai = (b * C + c) * Ss + s;
@@ -141,10 +147,11 @@ extern "C" int mmnc_gc_forward(const float *y, const float *scales, const float 
     MMNC_REQUIRE(B >= 0 && C >= 0 && Sy >= 0 && Ss >= 0, "gc_forward: negative dimension");
     MMNC_REQUIRE(Sy == Ss || Sy == 1, "gc_forward: y spatial size must equal the scales' or be 1 (got %lld vs %lld)",
                  (long long)Sy, (long long)Ss);
-    MMNC_REQUIRE(noise_mode >= 0 && noise_mode <= 3, "gc_forward: bad noise_mode %d", noise_mode);
+    MMNC_REQUIRE(noise_mode >= 0 && noise_mode <= 4, "gc_forward: bad noise_mode %d", noise_mode);
     if (B * C * Ss == 0) return MMNC_OK;
     MMNC_REQUIRE(y && scales && y_hat && lik, "gc_forward: null pointer");
-    MMNC_REQUIRE(noise_mode != MMNC_QUANT_NOISE_GIVEN || noise, "gc_forward: noise_mode GIVEN needs noise");
+    MMNC_REQUIRE((noise_mode != MMNC_QUANT_NOISE_GIVEN && noise_mode != MMNC_QUANT_NOISE_PHILOX_DEV) || noise,
+                 "gc_forward: this noise_mode needs the noise pointer");
     dim3 grid((unsigned)C, (unsigned)gc_splits(C, B * Ss));
     gc_forward_kernel<<<grid, GC_THREADS, 0, as_stream(stream)>>>(y, scales, means, B, C, Sy, Ss, noise_mode,
                                                                    noise, seed, offset, scale_bound,

@@ -10,7 +10,7 @@
 // chunks of 16 accumulators per thread; the chunk's column block of gamma sits in shared memory and is read as
 // broadcast float4s (16 FMAs per 4 LDS.128 + 1 LDG that hits L1 after the first chunk).
 #include "common.cuh"
-#include "hd_math.cuh"
+#include "gdn_params.cuh"
 
 namespace mmnc {
 
@@ -23,8 +23,7 @@ constexpr int GDN_CH = 16;   // output channels per chunk
 template <int MODE>
 __global__ void __launch_bounds__(GDN_TP)
 gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t NP, int C, int64_t HW,
-                const float *__restrict__ beta, const float *__restrict__ gamma, int inverse, float *out,
-                float *U) {
+                const GdnParams prm, int inverse, float *out, float *U) {
     extern __shared__ __align__(16) float W[];  // [C][GDN_CH]
     const int nchunks = (C + GDN_CH - 1) / GDN_CH;
     const float pcoef = inverse ? 0.5f : -0.5f;
@@ -40,10 +39,10 @@ gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_
             for (int idx = threadIdx.x; idx < C * GDN_CH; idx += GDN_TP) {
                 if (MODE == 2) {  // W[i][kk] = gamma[i][i0 + kk]
                     const int i = idx / GDN_CH, kk = idx - i * GDN_CH;
-                    W[idx] = (i0 + kk < C) ? gamma[(int64_t)i * C + i0 + kk] : 0.f;
+                    W[idx] = (i0 + kk < C) ? prm.g((int64_t)i * C + i0 + kk) : 0.f;
                 } else {          // W[j][ii] = gamma[i0 + ii][j]
                     const int ii = idx / C, j = idx - ii * C;
-                    W[j * GDN_CH + ii] = (i0 + ii < C) ? gamma[(int64_t)(i0 + ii) * C + j] : 0.f;
+                    W[j * GDN_CH + ii] = (i0 + ii < C) ? prm.g((int64_t)(i0 + ii) * C + j) : 0.f;
                 }
             }
             __syncthreads();
@@ -74,7 +73,7 @@ gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_
                 if (MODE == 2) {
                     out[a] += 2.f * xi * acc[ii];
                 } else {
-                    const float n = beta[i] + acc[ii];
+                    const float n = prm.b(i) + acc[ii];
                     const float rt = sqrtf(n);
                     const float pw = inverse ? rt : 1.f / rt;  // n^p
                     if (MODE == 0) {
@@ -156,21 +155,22 @@ gdn_dgamma_kernel(const float *__restrict__ U, const float *__restrict__ x, int6
 }
 
 __global__ void __launch_bounds__(256)
-gdn_reduce_kernel(const float *__restrict__ part, int ksplit, int C, float *__restrict__ dgamma,
-                  float *__restrict__ dbeta) {
+gdn_reduce_kernel(const float *__restrict__ part, int ksplit, int C, const GdnParams prm,
+                  float *__restrict__ dgamma, float *__restrict__ dbeta) {
     const int CJ = C + 1;
     const int64_t n = (int64_t)C * CJ;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < ksplit; ++k) s += part[(int64_t)k * n + e];
         const int i = (int)(e / CJ), j = (int)(e - (int64_t)i * CJ);
-        if (j < C) dgamma[(int64_t)i * C + j] = s; else dbeta[i] = s;
+        if (j < C) dgamma[(int64_t)i * C + j] = prm.dg((int64_t)i * C + j, s); else dbeta[i] = prm.db(i, s);
     }
 }
 
-int gdn_reduce_partials(const float *part, int ksplit, int C, float *dgamma, float *dbeta, cudaStream_t s) {
+int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &prm, float *dgamma, float *dbeta,
+                        cudaStream_t s) {
     const int64_t n = (int64_t)C * (C + 1);
-    gdn_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, ksplit, C, dgamma, dbeta);
+    gdn_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
     return after_launch("gdn_reduce_kernel");
 }
 
@@ -196,15 +196,15 @@ static inline int dgamma_ksplit(int64_t NP, int C) {
     return (int)ks;
 }
 
-int gdn_simt_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta, const float *gamma,
-                     int inverse, float *y, cudaStream_t s) {
+int gdn_simt_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, float *y,
+                     cudaStream_t s) {
     const int64_t NP = B * HW;
     const SimtGrid gr = simt_grid(NP, (int)C);
     const size_t smem = sizeof(float) * (size_t)C * GDN_CH;
     if (smem > 48 * 1024)
         MMNC_CUDA(cudaFuncSetAttribute(gdn_simt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gdn_simt_kernel<0><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, nullptr, NP, (int)C, HW, beta, gamma,
-                                                                     inverse, y, nullptr);
+    gdn_simt_kernel<0><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, nullptr, NP, (int)C, HW, prm, inverse, y,
+                                                                     nullptr);
     return after_launch("gdn_simt_kernel<fwd>");
 }
 
@@ -214,9 +214,9 @@ size_t gdn_simt_backward_workspace(int64_t B, int64_t C, int64_t HW) {
     return sizeof(float) * ((size_t)(B * C * HW) + (size_t)ks * C * (C + 1)) + 256;
 }
 
-int gdn_simt_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
-                      const float *gamma, int inverse, float *dx, float *dbeta, float *dgamma, void *workspace,
-                      size_t workspace_bytes, cudaStream_t s) {
+int gdn_simt_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
+                      int inverse, float *dx, float *dbeta, float *dgamma, void *workspace, size_t workspace_bytes,
+                      cudaStream_t s) {
     const int64_t NP = B * HW;
     MMNC_REQUIRE(workspace_bytes >= gdn_simt_backward_workspace(B, C, HW), "gdn_backward: workspace too small");
     float *U = static_cast<float *>(workspace);
@@ -227,9 +227,9 @@ int gdn_simt_backward(const float *x, const float *g, int64_t B, int64_t C, int6
         MMNC_CUDA(cudaFuncSetAttribute(gdn_simt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MMNC_CUDA(cudaFuncSetAttribute(gdn_simt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    gdn_simt_kernel<1><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, g, NP, (int)C, HW, beta, gamma, inverse, dx, U);
+    gdn_simt_kernel<1><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, g, NP, (int)C, HW, prm, inverse, dx, U);
     if (int rc = after_launch("gdn_simt_kernel<bwd1>")) return rc;
-    gdn_simt_kernel<2><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, g, NP, (int)C, HW, beta, gamma, inverse, dx, U);
+    gdn_simt_kernel<2><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, g, NP, (int)C, HW, prm, inverse, dx, U);
     if (int rc = after_launch("gdn_simt_kernel<bwd2>")) return rc;
     const int ks = dgamma_ksplit(NP, (int)C);
     int64_t kper = (NP + ks - 1) / ks;
@@ -237,9 +237,7 @@ int gdn_simt_backward(const float *x, const float *g, int64_t B, int64_t C, int6
     const int tiles = (int)(((C + DG_T - 1) / DG_T) * ((C + 1 + DG_T - 1) / DG_T));
     gdn_dgamma_kernel<<<dim3((unsigned)tiles, (unsigned)ks), 256, 0, s>>>(U, x, NP, (int)C, HW, kper, part);
     if (int rc = after_launch("gdn_dgamma_kernel")) return rc;
-    const int64_t n = C * (C + 1);
-    gdn_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, ks, (int)C, dgamma, dbeta);
-    return after_launch("gdn_reduce_kernel");
+    return gdn_reduce_partials(part, ks, (int)C, prm, dgamma, dbeta, s);
 }
 
 }  // namespace mmnc

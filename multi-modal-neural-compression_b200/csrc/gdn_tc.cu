@@ -16,6 +16,7 @@
 // MMNC_GDN_3XTF32 = hi/lo split of both operands, three passes (hi*hi + lo*hi + hi*lo), fp32-class accuracy.
 // The tensor pipe has so much headroom over HBM here that even three passes stay memory-bound.
 #include "common.cuh"
+#include "gdn_params.cuh"
 #include "tc_ptx.cuh"
 
 namespace mmnc {
@@ -112,8 +113,8 @@ __device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float 
 
 template <bool k3x, int KP8, bool kBetaInMma>
 __global__ void __launch_bounds__(tc::TILE_M)
-gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const float *__restrict__ beta,
-                      const float *__restrict__ gamma, int inverse, float *__restrict__ y, int C, int Np, int d_col_i,
+gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const GdnParams prm, int inverse,
+                      float *__restrict__ y, int C, int Np, int d_col_i,
                       uint32_t tmem_cols, uint32_t b_bytes) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -131,14 +132,14 @@ gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const
     constexpr int kcores = Kp >> 2;
     for (int idx = threadIdx.x; idx < Np * Kp; idx += TILE_M) {
         const int n = idx / Kp, k = idx - n * Kp;
-        float g = (n < C && k < C) ? gamma[(int64_t)n * C + k] : 0.f;
-        if (kBetaInMma && k == Kp - 1) g = (n < C) ? beta[n] : 1.f;
+        float g = (n < C && k < C) ? prm.g((int64_t)n * C + k) : 0.f;
+        if (kBetaInMma && k == Kp - 1) g = (n < C) ? prm.b(n) : 1.f;
         const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
         const uint32_t hi = to_tf32(g);
         reinterpret_cast<uint32_t *>(Bs_hi)[off] = hi;
         if (k3x) reinterpret_cast<uint32_t *>(Bs_lo)[off] = to_tf32(g - __uint_as_float(hi));
     }
-    for (int i = threadIdx.x; i < Np; i += TILE_M) beta_s[i] = (i < C) ? beta[i] : 1.f;
+    for (int i = threadIdx.x; i < Np; i += TILE_M) beta_s[i] = (i < C) ? prm.b(i) : 1.f;
     fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
     fence_before();
     __syncthreads();
@@ -193,8 +194,8 @@ bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision) {
     return tc_geometry(C, precision == MMNC_GDN_3XTF32, &g) && C >= 16 && B * HW >= 4096;
 }
 
-int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta, const float *gamma,
-                   int inverse, int precision, float *y, cudaStream_t s) {
+int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, int precision,
+                   float *y, cudaStream_t s) {
     tc::Geometry g;
     const bool k3x = (precision == MMNC_GDN_3XTF32);
     if (!tc_geometry(C, k3x, &g)) {
@@ -215,8 +216,8 @@ int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float
         set_error("gdn_tc_forward: gamma does not fit shared memory for C = %lld", (long long)C);
         return MMNC_ERR_UNSUPPORTED;
     }
-    using Kernel = void (*)(const float *, int64_t, int64_t, const float *, const float *, int, float *, int, int, int,
-                            uint32_t, uint32_t);
+    using Kernel = void (*)(const float *, int64_t, int64_t, const GdnParams, int, float *, int, int, int, uint32_t,
+                            uint32_t);
     Kernel kernel = nullptr;
     const bool beta_in_mma = (C % 8) != 0;
 #define MMNC_TC_CASE(N)                                                                                        \
@@ -238,7 +239,7 @@ int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const float
     MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = (int64_t)sm_count() * (max_ctas < 4 ? max_ctas : 4);
     if (grid > tiles) grid = tiles;
-    kernel<<<(unsigned)grid, tc::TILE_M, smem, s>>>(x, NP, HW, beta, gamma, inverse, y, g.C, g.Np, g.d_col, g.tmem_cols,
+    kernel<<<(unsigned)grid, tc::TILE_M, smem, s>>>(x, NP, HW, prm, inverse, y, g.C, g.Np, g.d_col, g.tmem_cols,
                                                     (uint32_t)g.b_bytes);
     return after_launch(k3x ? "gdn_tc_forward_kernel<3xtf32>" : "gdn_tc_forward_kernel<tf32>");
 }

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gdn_params.cuh"
 #include "tc_ptx.cuh"
 
 namespace mmnc {
@@ -212,7 +213,7 @@ __device__ __forceinline__ bool gdn_tc_bwd_loop(const float *__restrict__ x, con
 template <int KH8, bool kInverse>
 __global__ void __launch_bounds__(tcb::THREADS)
 gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t NP, int64_t HW,
-                       const float *__restrict__ beta, const float *__restrict__ gamma,
+                       const GdnParams prm,
                        float *__restrict__ dx, float *__restrict__ part, int C, uint32_t tmem_cols) {
     using namespace tc;
     using namespace tcb;
@@ -239,14 +240,14 @@ gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g,
     for (int idx = threadIdx.x; idx < P * P; idx += THREADS) {
         const int n = idx / P, k = idx - n * P;
         float v = 0.f;
-        if (n < C && k < C) v = gamma[(int64_t)n * C + k];
-        else if (n < C && k == C) v = beta[n];
+        if (n < C && k < C) v = prm.g((int64_t)n * C + k);
+        else if (n < C && k == C) v = prm.b(n);
         else if (n >= C && k == C) v = 1.f;  // padded outputs get norm = 1 (finite)
         const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
         reinterpret_cast<uint32_t *>(Bs)[off] = to_tf32(v);
         // transposed copy for MMA2 (a K-major operand again; tf32 MN-major reads of the same tile returned zeros
         // on sm_100a, so the transpose is materialised once per CTA instead)
-        const float vt = (n < C && k < C) ? gamma[(int64_t)k * C + n] : 0.f;
+        const float vt = (n < C && k < C) ? prm.g((int64_t)k * C + n) : 0.f;
         reinterpret_cast<uint32_t *>(Bs2)[off] = to_tf32(vt);
     }
     // rows of the two pixel-major operands that no thread writes (r in [P', 8 R8)) must stay finite: zero them
@@ -299,7 +300,8 @@ gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g,
 }
 
 // fixed-order reduction of per-CTA partials [ksplit][C][C+1] -> d gamma, d beta (gdn_simt.cu)
-int gdn_reduce_partials(const float *part, int ksplit, int C, float *dgamma, float *dbeta, cudaStream_t s);
+int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &prm, float *dgamma, float *dbeta,
+                        cudaStream_t s);
 
 static bool tcb_geometry(int64_t C, int *P, uint32_t *tmem_cols, size_t *smem) {
     if (C < 16 || C > 111) return false;
@@ -346,9 +348,9 @@ size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW) {
     return sizeof(float) * (size_t)tcb_grid(B * HW, cols, smem) * C * (C + 1) + 256;
 }
 
-int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
-                    const float *gamma, int inverse, float *dx, float *dbeta, float *dgamma, void *workspace,
-                    size_t workspace_bytes, cudaStream_t s) {
+int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
+                    int inverse, float *dx, float *dbeta, float *dgamma, void *workspace, size_t workspace_bytes,
+                    cudaStream_t s) {
     int P;
     uint32_t cols;
     size_t smem;
@@ -363,8 +365,8 @@ int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_
     const int max_ctas = 512 / (int)cols;
     const size_t min_smem = (227 * 1024) / (size_t)(max_ctas + 1) + 1;
     if (smem < min_smem) smem = min_smem;
-    using Kernel = void (*)(const float *, const float *, int64_t, int64_t, const float *, const float *, float *,
-                            float *, int, uint32_t);
+    using Kernel = void (*)(const float *, const float *, int64_t, int64_t, const GdnParams, float *, float *, int,
+                            uint32_t);
     Kernel kernel = nullptr;
 #define MMNC_CASE(N) case N: kernel = inverse ? (Kernel)gdn_tc_backward_kernel<N, true> : (Kernel)gdn_tc_backward_kernel<N, false>; break;
     switch (P / 16) {
@@ -378,9 +380,9 @@ int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_
     }
     MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float *part = static_cast<float *>(workspace);
-    kernel<<<(unsigned)grid, tcb::THREADS, smem, s>>>(x, g, NP, HW, beta, gamma, dx, part, (int)C, cols);
+    kernel<<<(unsigned)grid, tcb::THREADS, smem, s>>>(x, g, NP, HW, prm, dx, part, (int)C, cols);
     if (int rc = after_launch("gdn_tc_backward_kernel")) return rc;
-    return gdn_reduce_partials(part, grid, (int)C, dgamma, dbeta, s);
+    return gdn_reduce_partials(part, grid, (int)C, prm, dgamma, dbeta, s);
 }
 
 }  // namespace mmnc

@@ -26,6 +26,11 @@ __device__ __forceinline__ float mean_at(const float *means, int mode, int64_t i
 __global__ void __launch_bounds__(Q_THREADS)
 quantize_noise_kernel(const float *__restrict__ x, int64_t n, int noise_mode, const float *__restrict__ noise,
                       uint64_t seed, uint64_t offset, float *__restrict__ out) {
+    if (noise_mode == MMNC_QUANT_NOISE_PHILOX_DEV) {
+        const uint64_t *st = reinterpret_cast<const uint64_t *>(noise);
+        seed = st[0];
+        offset += st[1];
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float u = (noise_mode == MMNC_QUANT_NOISE_GIVEN) ? noise[i]
                                                                 : philox_uniform_centered(seed, (uint64_t)i + offset);
@@ -68,11 +73,11 @@ using namespace mmnc;
 extern "C" int mmnc_quantize_noise(const float *x, int64_t n, int noise_mode, const float *noise, uint64_t seed,
                                    uint64_t offset, float *out, void *stream) {
     MMNC_REQUIRE(n >= 0, "quantize_noise: negative size");
-    MMNC_REQUIRE(noise_mode == MMNC_QUANT_NOISE_PHILOX || noise_mode == MMNC_QUANT_NOISE_GIVEN,
-                 "quantize_noise: bad noise_mode %d", noise_mode);
+    MMNC_REQUIRE(noise_mode == MMNC_QUANT_NOISE_PHILOX || noise_mode == MMNC_QUANT_NOISE_GIVEN ||
+                     noise_mode == MMNC_QUANT_NOISE_PHILOX_DEV, "quantize_noise: bad noise_mode %d", noise_mode);
     if (n == 0) return MMNC_OK;
     MMNC_REQUIRE(x && out, "quantize_noise: null pointer");
-    MMNC_REQUIRE(noise_mode != MMNC_QUANT_NOISE_GIVEN || noise, "quantize_noise: needs noise");
+    MMNC_REQUIRE(noise_mode == MMNC_QUANT_NOISE_PHILOX || noise, "quantize_noise: needs the noise pointer");
     quantize_noise_kernel<<<q_blocks(n), Q_THREADS, 0, as_stream(stream)>>>(x, n, noise_mode, noise, seed, offset, out);
     return after_launch("quantize_noise_kernel");
 }

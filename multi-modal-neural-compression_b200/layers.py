@@ -69,6 +69,7 @@ class GDN(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         if x.dim() != 4:
             raise ValueError(f"GDN expects (B, C, H, W), got {tuple(x.shape)}")
-        beta = self.beta_reparam(self.beta)
-        gamma = self.gamma_reparam(self.gamma)
-        return ops.gdn(x, beta, gamma, self.inverse, self.precision)
+        # NonNegativeParametrizer (both parameters share the pedestal 2^-36) is applied inside the kernels
+        return ops.gdn_raw(x, self.beta, self.gamma, self.beta_reparam.lower_bound.value(),
+                           self.gamma_reparam.lower_bound.value(), self.beta_reparam._pedestal_f, self.inverse,
+                           self.precision)

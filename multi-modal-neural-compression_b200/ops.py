@@ -13,7 +13,7 @@ from torch import Tensor
 
 from . import _lib
 
-QUANT_DEQUANTIZE, QUANT_NOISE_PHILOX, QUANT_NOISE_GIVEN, QUANT_IDENTITY = 0, 1, 2, 3
+QUANT_DEQUANTIZE, QUANT_NOISE_PHILOX, QUANT_NOISE_GIVEN, QUANT_IDENTITY, QUANT_NOISE_PHILOX_DEV = 0, 1, 2, 3, 4
 MEANS_NONE, MEANS_PER_CHANNEL, MEANS_FULL = 0, 1, 2
 EB_FORM = {"sign": 0, "plain": 1}
 GDN_PRECISION = {"fp32": 0, "tf32": 1, "3xtf32": 2, "auto": 3}
@@ -61,9 +61,30 @@ class _NoiseSeed:
     def __init__(self):
         self.calls = 0
         self.rank, self.world_size = 0, 1
+        self.state: Optional[Tensor] = None
+        self.slot = 0
 
     def configure(self, rank: int = 0, world_size: int = 1) -> None:
         self.rank, self.world_size = int(rank), int(world_size)
+
+    # ---- device-resident (seed, offset): lets a captured CUDA graph draw fresh noise on every replay
+    def enable_device_state(self, device, seed: int = 21) -> None:
+        self.state = torch.tensor([int(seed), 0], dtype=torch.int64, device=device)
+        self.slot = 0
+
+    def disable_device_state(self) -> None:
+        self.state = None
+
+    def step(self) -> None:
+        """Advance the device-side stream (call once per training step, inside the captured region)."""
+        if self.state is not None:
+            self.state[0:1].add_(1)
+            self.slot = 0
+
+    def next_device(self, numel: int) -> Tuple[Tensor, int]:
+        """-> (state tensor, host offset): every call inside a step gets its own 2^40-element slot."""
+        self.slot += 1
+        return self.state, self.slot * (1 << 40) + self.rank * int(numel)
 
     def next(self, numel: int = 0) -> Tuple[int, int]:
         # The seed follows torch's CPU generator, so torch.manual_seed() makes runs reproducible and ranks seeded
@@ -77,11 +98,14 @@ noise_source = _NoiseSeed()
 
 
 # ------------------------------------------------------------------------------------------------ quantise (a2)
-def quantize_noise(x: Tensor, noise: Optional[Tensor] = None, seed: Optional[int] = None, offset: int = 0) -> Tensor:
+def quantize_noise(x: Tensor, noise: Optional[Tensor] = None, seed: Optional[int] = None, offset: int = 0,
+                   state: Optional[Tensor] = None) -> Tensor:
     _need_cuda(x, noise)
     x = _f32c(x)
     out = torch.empty_like(x)
-    if noise is not None:
+    if state is not None:  # device-resident (seed, offset)
+        mode, noise, seed = QUANT_NOISE_PHILOX_DEV, state, 0
+    elif noise is not None:
         mode, noise = QUANT_NOISE_GIVEN, _f32c(noise.expand_as(x))
         seed = 0
     else:
@@ -140,7 +164,8 @@ class _EntropyBottleneckFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, packed, medians, mode, noise, seed, offset, bound, form):
         _need_cuda(x, packed, medians, noise)
-        x, packed, medians, noise = _f32c(x), _f32c(packed), _f32c(medians), _f32c(noise)
+        x, packed, medians = _f32c(x), _f32c(packed), _f32c(medians)
+        noise = noise if mode == QUANT_NOISE_PHILOX_DEV else _f32c(noise)
         B, C, S = _bcs(x)
         if packed.shape != (C, EB_NP):
             raise ValueError(f"packed EB parameters must be ({C}, {EB_NP}), got {tuple(packed.shape)}")
@@ -178,6 +203,9 @@ def entropy_bottleneck_forward(x: Tensor, packed: Tensor, medians: Tensor, train
         mode = QUANT_DEQUANTIZE
     elif noise is not None:
         mode, noise = QUANT_NOISE_GIVEN, noise.expand_as(x)
+    elif seed is None and noise_source.state is not None:
+        mode = QUANT_NOISE_PHILOX_DEV
+        noise, offset = noise_source.next_device(x.numel())
     else:
         mode = QUANT_NOISE_PHILOX
         if seed is None:
@@ -222,7 +250,8 @@ class _GaussianConditionalFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, scales, means, mode, noise, seed, offset, scale_bound, lik_bound):
         _need_cuda(y, scales, means, noise)
-        y, scales, means, noise = _f32c(y), _f32c(scales), _f32c(means), _f32c(noise)
+        y, scales, means = _f32c(y), _f32c(scales), _f32c(means)
+        noise = noise if mode == QUANT_NOISE_PHILOX_DEV else _f32c(noise)
         B, C, Sy = _bcs(y)
         B2, C2, Ss = _bcs(scales)
         if (B, C) != (B2, C2) or not (Sy == Ss or Sy == 1):
@@ -266,6 +295,9 @@ def gaussian_conditional_forward(y: Tensor, scales: Tensor, means: Optional[Tens
         mode = QUANT_DEQUANTIZE
     elif noise is not None:
         mode, noise = QUANT_NOISE_GIVEN, noise.expand_as(y)
+    elif seed is None and noise_source.state is not None:
+        mode = QUANT_NOISE_PHILOX_DEV
+        noise, offset = noise_source.next_device(y.numel())
     else:
         mode = QUANT_NOISE_PHILOX
         if seed is None:
@@ -276,6 +308,8 @@ def gaussian_conditional_forward(y: Tensor, scales: Tensor, means: Optional[Tens
     # general broadcasting: quantise y in its own shape, then evaluate on the materialised broadcast
     if mode == QUANT_DEQUANTIZE:
         y_hat = _StraightRound.apply(y, means)
+    elif mode == QUANT_NOISE_PHILOX_DEV:
+        y_hat = _AddNoise.apply(y, None, None, offset, noise)
     else:
         y_hat = _AddNoise.apply(y, noise, seed, offset)
     yb, sb = torch.broadcast_tensors(y_hat, scales)
@@ -289,12 +323,12 @@ class _AddNoise(torch.autograd.Function):
     """x + U(-1/2, 1/2) (or + given noise) with d/dx = 1."""
 
     @staticmethod
-    def forward(ctx, x, noise, seed, offset):
-        return quantize_noise(x, noise=noise, seed=seed, offset=offset)
+    def forward(ctx, x, noise, seed, offset, state=None):
+        return quantize_noise(x, noise=noise, seed=seed, offset=offset, state=state)
 
     @staticmethod
     def backward(ctx, g):
-        return g, None, None, None
+        return g, None, None, None, None
 
 
 class _StraightRound(torch.autograd.Function):
@@ -454,6 +488,45 @@ class _GDNFn(torch.autograd.Function):
         _lib.check(_lib.lib().mmnc_gdn_backward(_p(x), _p(g), B, C, HW, _p(beta), _p(gamma), inverse, precision, _p(dx),
                                                 _p(dbeta), _p(dgamma), _p(ws), nbytes, _stream()))
         return dx, dbeta, dgamma, None, None
+
+
+class _GDNRawFn(torch.autograd.Function):
+    """GDN on the raw `beta` / `gamma` parameters: the re-parametrisation and its LowerBound gradient are fused
+    into the contraction kernels (1 launch forward, 2 backward)."""
+
+    @staticmethod
+    def forward(ctx, x, beta, gamma, beta_bound, gamma_bound, pedestal, inverse, precision):
+        _need_cuda(x, beta, gamma)
+        x, beta, gamma = _f32c(x), _f32c(beta), _f32c(gamma)
+        B, C, HW = _bcs(x)
+        if beta.numel() != C or gamma.shape != (C, C):
+            raise ValueError(f"GDN parameters do not match {C} channels")
+        y = torch.empty_like(x)
+        _lib.check(_lib.lib().mmnc_gdn_forward_raw(_p(x), B, C, HW, _p(beta), _p(gamma), beta_bound, gamma_bound,
+                                                   pedestal, int(inverse), precision, _p(y), _stream()))
+        ctx.save_for_backward(x, beta, gamma)
+        ctx.cfg = (B, C, HW, int(inverse), precision, beta_bound, gamma_bound, pedestal)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, beta, gamma = ctx.saved_tensors
+        B, C, HW, inverse, precision, bb, gb, ped = ctx.cfg
+        g = _f32c(g)
+        dx = torch.empty_like(x)
+        dbeta, dgamma = torch.empty_like(beta), torch.empty_like(gamma)
+        nbytes = int(_lib.lib().mmnc_gdn_backward_workspace_bytes(B, C, HW, precision))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.check(_lib.lib().mmnc_gdn_backward_raw(_p(x), _p(g), B, C, HW, _p(beta), _p(gamma), bb, gb, ped, inverse,
+                                                    precision, _p(dx), _p(dbeta), _p(dgamma), _p(ws), nbytes,
+                                                    _stream()))
+        return dx, dbeta, dgamma, None, None, None, None, None
+
+
+def gdn_raw(x: Tensor, beta: Tensor, gamma: Tensor, beta_bound: float, gamma_bound: float, pedestal: float,
+            inverse: bool, precision: str = "auto") -> Tensor:
+    return _GDNRawFn.apply(x, beta, gamma, float(beta_bound), float(gamma_bound), float(pedestal), bool(inverse),
+                           GDN_PRECISION[precision])
 
 
 def gdn(x: Tensor, beta_eff: Tensor, gamma_eff: Tensor, inverse: bool, precision: str = "auto") -> Tensor:
