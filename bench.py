@@ -502,9 +502,14 @@ def run_b200(args):
         line.update(extra)
         if "cpu_baseline" not in line:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without running NCCL / CUDA-graph destructors: tearing down a communicator that was captured in a
+        # CUDA graph hung the 2-GPU run at exit.  Everything has been synchronised and printed by now.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
