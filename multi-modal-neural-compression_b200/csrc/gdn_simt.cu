@@ -154,23 +154,32 @@ gdn_dgamma_kernel(const float *__restrict__ U, const float *__restrict__ x, int6
     }
 }
 
+// one warp per output element: lanes stride over the partials, then a shuffle tree — a fixed summation order
 __global__ void __launch_bounds__(256)
 gdn_reduce_kernel(const float *__restrict__ part, int ksplit, int C, const GdnParams prm,
                   float *__restrict__ dgamma, float *__restrict__ dbeta) {
     const int CJ = C + 1;
     const int64_t n = (int64_t)C * CJ;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n;
+         e += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         float s = 0.f;
-        for (int k = 0; k < ksplit; ++k) s += part[(int64_t)k * n + e];
-        const int i = (int)(e / CJ), j = (int)(e - (int64_t)i * CJ);
-        if (j < C) dgamma[(int64_t)i * C + j] = prm.dg((int64_t)i * C + j, s); else dbeta[i] = prm.db(i, s);
+        for (int k = lane; k < ksplit; k += 32) s += part[(int64_t)k * n + e];
+        s = warp_sum(s);
+        if (lane == 0) {
+            const int i = (int)(e / CJ), j = (int)(e - (int64_t)i * CJ);
+            if (j < C) dgamma[(int64_t)i * C + j] = prm.dg((int64_t)i * C + j, s); else dbeta[i] = prm.db(i, s);
+        }
     }
 }
 
 int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &prm, float *dgamma, float *dbeta,
                         cudaStream_t s) {
     const int64_t n = (int64_t)C * (C + 1);
-    gdn_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
+    int64_t blocks = (n + 7) / 8;  // 8 warps per block, one element per warp
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    gdn_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
     return after_launch("gdn_reduce_kernel");
 }
 
