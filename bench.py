@@ -371,6 +371,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device — this arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True  # let cuDNN pick its conv algorithms for the fixed shapes (convs are out of scope)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(21)
