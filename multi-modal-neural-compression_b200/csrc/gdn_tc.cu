@@ -48,11 +48,12 @@ __device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float 
     constexpr uint32_t a_hi = 0, a_lo = (uint32_t)Kp;
     // ---- all of the pixel's channels in flight at once (one DRAM round trip per tile), kept in registers.
     // Padded channels (c >= C) re-read the last real channel: their B rows are zero, so any finite value works.
+    const uint32_t sb = (uint32_t)HW * 4u;  // channel stride in bytes
     float xv[Kp];
 #pragma unroll
     for (int c = 0; c < Kp; ++c) {
         const int cc = (c < Kp - 8) ? c : ((c < C) ? c : C - 1);
-        xv[c] = (kFull || valid) ? __ldcs(xb + (int64_t)cc * HW) : 0.f;
+        xv[c] = (kFull || valid) ? __ldcs(chan_ptr(xb, sb, cc)) : 0.f;
     }
     // ---- A operand: x^2 -> tf32 -> TMEM (lane = pixel, column = channel)
 #pragma unroll
@@ -102,7 +103,7 @@ __device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float 
                 const float rs = fast_rsqrt(n);
                 const float out = xv[i] * (inverse ? n * rs : rs);
                 const bool ok = (kFull || valid) && (i < Kp - 8 || i < C);
-                if (ok) __stcs(yb + (int64_t)i * HW, out);
+                if (ok) __stcs(chan_ptr(yb, sb, i), out);
             }
         }
     }
@@ -191,7 +192,7 @@ static bool tc_geometry(int64_t C, bool k3x, tc::Geometry *g) {
 bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision) {
     tc::Geometry g;
     // small problems stay on the SIMT kernel: a tile is 128 pixels and the B operand is staged once per CTA
-    return tc_geometry(C, precision == MMNC_GDN_3XTF32, &g) && C >= 16 && B * HW >= 4096;
+    return tc_geometry(C, precision == MMNC_GDN_3XTF32, &g) && C >= 16 && B * HW >= 4096 && HW < (1 << 24);
 }
 
 int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, int precision,

@@ -63,6 +63,7 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
     constexpr int SAFE = P - 16;       // channels below this are always real (C > P - 16)
     constexpr uint32_t a_col = 0, d_col = (uint32_t)P, d3_col = (uint32_t)(2 * P);
     const bool ok = kFull || valid;
+    const uint32_t sb = (uint32_t)HW * 4u;  // channel stride in bytes
     // swizzled shared-memory offsets: row c = c_begin + j0 + j with j0, c_begin multiples of 8, so (c & 7) == j and
     // (c >> 3) is a constant: one register per j holds the thread-dependent part, the row group is an immediate
     uint32_t soff[8];
@@ -74,6 +75,7 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
                                  ((p32 & 3) << 2));
     }
     const int rows = 8 * R8;  // rows that exist in ubuf / x2buf
+    const uint32_t us = smem_u32(ubuf), x2s = smem_u32(x2buf);
 
     // ---- loads: this thread's channels of x and g, all in flight (32-bit element offsets from a per-pixel base)
     float xv[KH], gv[KH];
@@ -81,8 +83,8 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
     for (int j = 0; j < KH; ++j) {
         const int c = c_begin + j;
         const int cc = (c < SAFE) ? c : ((c < C) ? c : C - 1);  // padded channels re-read a real one (weights are 0)
-        xv[j] = ok ? __ldcs(xb + cc * HW) : 0.f;
-        gv[j] = ok ? __ldcs(gb + cc * HW) : 0.f;
+        xv[j] = ok ? __ldcs(chan_ptr(xb, sb, cc)) : 0.f;
+        gv[j] = ok ? __ldcs(chan_ptr(gb, sb, cc)) : 0.f;
     }
     // ---- x^2 -> A (TMEM) and -> x2buf (smem, K = pixel); padded channel C is the constant 1
 #pragma unroll
@@ -94,7 +96,7 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
             float sq = xv[j0 + j] * xv[j0 + j];
             if (c >= SAFE) sq = (c < C) ? sq : ((c == C) ? 1.f : 0.f);
             v[j] = to_tf32(sq);
-            if (c < SAFE || c < rows) *reinterpret_cast<uint32_t *>(x2buf + soff[j] + (j0 << 7)) = v[j];
+            if (c < SAFE || c < rows) st_shared_u32(x2s + soff[j] + (j0 << 7), v[j]);
         }
         tmem_st8(lane_base + a_col + c_begin + j0, v);
     }
@@ -133,7 +135,7 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
             if (!kFull && !valid) u = 0.f;
             gv[j0 + j] = gv[j0 + j] * pw;
             uu[j] = to_tf32(u);
-            if (c < SAFE || c < rows) *reinterpret_cast<uint32_t *>(ubuf + soff[j] + (j0 << 7)) = uu[j];
+            if (c < SAFE || c < rows) st_shared_u32(us + soff[j] + (j0 << 7), uu[j]);
         }
         tmem_st8(lane_base + a_col + c_begin + j0, uu);
     }
@@ -169,7 +171,7 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
         for (int j = 0; j < 8; ++j) {
             const int c = c_begin + j0 + j;
             const float out = fmaf(2.f * xv[j0 + j], __uint_as_float(r[j]), gv[j0 + j]);
-            if (ok && (c < SAFE || c < C)) __stcs(dxb + c * HW, out);
+            if (ok && (c < SAFE || c < C)) __stcs(chan_ptr(dxb, sb, c), out);
         }
     }
     fence_before();

@@ -58,6 +58,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ void st_shared_u32(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -74,6 +77,14 @@ __device__ __forceinline__ float fast_rsqrt(float v) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
+}
+
+// base + c * stride_bytes with a 32-bit stride: one IMAD.WIDE.U32 per address instead of a sign-extended 64-bit add chain
+__device__ __forceinline__ const float *chan_ptr(const float *base, uint32_t stride_bytes, int c) {
+    return reinterpret_cast<const float *>(reinterpret_cast<const char *>(base) + (uint64_t)stride_bytes * (uint32_t)c);
+}
+__device__ __forceinline__ float *chan_ptr(float *base, uint32_t stride_bytes, int c) {
+    return reinterpret_cast<float *>(reinterpret_cast<char *>(base) + (uint64_t)stride_bytes * (uint32_t)c);
 }
 
 __device__ __forceinline__ uint32_t to_tf32(float v) {
