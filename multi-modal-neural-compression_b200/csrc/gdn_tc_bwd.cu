@@ -85,6 +85,9 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
         const int cc = (c < SAFE) ? c : ((c < C) ? c : C - 1);  // padded channels re-read a real one (weights are 0)
         xv[j] = ok ? __ldcs(chan_ptr(xb, sb, cc)) : 0.f;
         gv[j] = ok ? __ldcs(chan_ptr(gb, sb, cc)) : 0.f;
+        // compile-time fence every 4 channels: keeps the address arithmetic next to its load instead of letting the
+        // scheduler materialise all 2 KH 64-bit addresses first (the loads still issue back to back)
+        if ((j & 3) == 3) asm volatile("" ::: "memory");
     }
     // ---- x^2 -> A (TMEM) and -> x2buf (smem, K = pixel); padded channel C is the constant 1
 #pragma unroll
@@ -213,7 +216,7 @@ __device__ __forceinline__ bool gdn_tc_bwd_loop(const float *__restrict__ x, con
 }
 
 template <int KH8, bool kInverse>
-__global__ void __launch_bounds__(tcb::THREADS)
+__global__ void __launch_bounds__(tcb::THREADS, (KH8 <= 4) ? 2 : 1)
 gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t NP, int64_t HW,
                        const GdnParams prm,
                        float *__restrict__ dx, float *__restrict__ part, int C, uint32_t tmem_cols) {
