@@ -54,6 +54,7 @@ __device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float 
     for (int c = 0; c < Kp; ++c) {
         const int cc = (c < Kp - 8) ? c : ((c < C) ? c : C - 1);
         xv[c] = (kFull || valid) ? __ldcs(chan_ptr(xb, sb, cc)) : 0.f;
+        if ((c & 7) == 7) asm volatile("" ::: "memory");  // keep address arithmetic next to its load (register pressure)
     }
     // ---- A operand: x^2 -> tf32 -> TMEM (lane = pixel, column = channel)
 #pragma unroll
@@ -112,8 +113,15 @@ __device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float 
     fence_after();
 }
 
+// CTAs per SM that TMEM admits for this instance (columns: A = Kp [x2 when split], D = Np <= Kp + 8; power-of-two alloc)
+template <bool k3x, int KP8>
+constexpr int tc_fwd_ctas() {
+    const int need = KP8 * 8 * (k3x ? 2 : 1) + (KP8 + 1) / 2 * 16;
+    return need <= 128 ? 4 : (need <= 256 ? 2 : 1);
+}
+
 template <bool k3x, int KP8, bool kBetaInMma>
-__global__ void __launch_bounds__(tc::TILE_M)
+__global__ void __launch_bounds__(tc::TILE_M, tc_fwd_ctas<k3x, KP8>())
 gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const GdnParams prm, int inverse,
                       float *__restrict__ y, int C, int Np, int d_col_i,
                       uint32_t tmem_cols, uint32_t b_bytes) {
