@@ -170,6 +170,10 @@ size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int p
 int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta,
                       const float *gamma, int inverse, int precision, float *dx, float *dbeta, float *dgamma,
                       void *workspace, size_t workspace_bytes, void *stream);
+/* Which kernel family mmnc_gdn_backward would launch for these arguments (diagnostics / tests):
+ * 0 = streaming (C <= 4), 1 = fp32 SIMT, 2 = fused tcgen05, 3 = fused tcgen05 fed by TMA and software-pipelined
+ * (needs HW % 128 == 0 and 16-byte aligned x / g). */
+int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, int precision);
 /* Same two calls taking the RAW parameters of compressai.layers.GDN (`beta`, `gamma` as stored in the state dict):
  * the NonNegativeParametrizer re-parametrisation (effective = max(p, bound)^2 - pedestal) is applied while the
  * kernels stage the parameters, and the gradients come back w.r.t. the raw parameters with LowerBound's custom

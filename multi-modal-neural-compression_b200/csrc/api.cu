@@ -49,6 +49,8 @@ int gdn_small_backward(const float *, const float *, int64_t, int64_t, int64_t, 
 // gdn_tc.cu
 bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision);
 int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, int, float *, cudaStream_t);
+// gdn_tc_bwd2.cu
+bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64_t C, int64_t HW);
 // gdn_tc_bwd.cu
 bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW);
 size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW);
@@ -105,6 +107,14 @@ extern "C" size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_
     const size_t a = gdn_simt_backward_workspace(B, C, HW), b = gdn_tc_backward_workspace(B, C, HW);
     const bool tc = (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW);
     return tc ? b : (a > b ? a : b);
+}
+
+extern "C" int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t B, int64_t C, int64_t HW,
+                                         int precision) {
+    if (gdn_small_supported(C)) return 0;
+    if ((precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW))
+        return gdn_tc_backward2_supported(x, g, B, C, HW) ? 3 : 2;
+    return 1;
 }
 
 static int gdn_backward_impl(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,

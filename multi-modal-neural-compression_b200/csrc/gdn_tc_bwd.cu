@@ -37,6 +37,23 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int p, int R8) {
 }
 }  // namespace tcb
 
+template <int KS, int NK>
+__device__ __forceinline__ void v1_ts_chain(uint32_t d, uint32_t a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if constexpr (KS < NK) {
+        tc::mma_tf32_ts_step<KS * 8, KS * 16>(d, a, b_lo, b_hi, idesc, KS > 0 ? 1u : 0u);
+        v1_ts_chain<KS + 1, NK>(d, a, b_lo, b_hi, idesc);
+    }
+}
+template <int KS>
+__device__ __forceinline__ void v1_ss_chain(uint32_t d3, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t atom16,
+                                            uint32_t idesc, uint32_t first_acc) {
+    if constexpr (KS < tcb::TILE / 8) {
+        tc::mma_tf32_ss_step<(KS & 3) * 2>(d3, a_lo, b_lo, hi, (uint32_t)(KS >> 2) * atom16, idesc,
+                                           KS == 0 ? first_acc : 1u);
+        v1_ss_chain<KS + 1>(d3, a_lo, b_lo, hi, atom16, idesc, first_acc);
+    }
+}
+
 // KH8 = (channels per thread) / 8 = P / 16.  HALF (which half of the channels), kInverse and kFull are template
 // parameters so that every channel index below is a compile-time constant: only the last 16 padded channels of
 // HALF 1 keep run-time checks against C, everything else is straight-line code with immediate offsets.
@@ -110,10 +127,8 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
     // ---- MMA1: D = x2 * gamma^T (+ beta through the constant column)
     if (threadIdx.x == 0) {
         fence_after();
-#pragma unroll
-        for (int ks = 0; ks < P / 8; ++ks)
-            mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + ks * 8, desc_b1 + (uint64_t)((ks * 256) >> 4), idesc,
-                        ks > 0 ? 1u : 0u);
+        // per-step descriptor offsets are immediates inside the asm (tc_ptx.cuh): nothing 64-bit to hoist and spill
+        v1_ts_chain<0, P / 8>(tmem_base + d_col, tmem_base + a_col, (uint32_t)desc_b1, (uint32_t)(desc_b1 >> 32), idesc);
         mma_commit(mbar);
     }
     mbar_wait(mbar, parity);
@@ -149,16 +164,9 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
     // ---- MMA2: D = u * gamma (B = gamma^T tile);  MMA3: D3 += u^T x2 (K = 128 pixels)
     if (threadIdx.x == 0) {
         fence_after();
-#pragma unroll
-        for (int ks = 0; ks < P / 8; ++ks)
-            mma_tf32_ts(tmem_base + d_col, tmem_base + a_col + ks * 8, desc_b2 + (uint64_t)((ks * 256) >> 4), idesc,
-                        ks > 0 ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < TILE / 8; ++ks) {
-            const uint32_t off = (uint32_t)((ks >> 2) * R8 * 1024 + (ks & 3) * 32);
-            mma_tf32_ss(tmem_base + d3_col, desc_a3 + (uint64_t)(off >> 4), desc_b3 + (uint64_t)(off >> 4), idesc,
-                        (first_tile && ks == 0) ? 0u : 1u);
-        }
+        v1_ts_chain<0, P / 8>(tmem_base + d_col, tmem_base + a_col, (uint32_t)desc_b2, (uint32_t)(desc_b2 >> 32), idesc);
+        v1_ss_chain<0>(tmem_base + d3_col, (uint32_t)desc_a3, (uint32_t)desc_b3, (uint32_t)(desc_a3 >> 32),
+                       (uint32_t)R8 * 64u, idesc, first_tile ? 0u : 1u);
         mma_commit(mbar);
     }
     mbar_wait(mbar, parity);
@@ -308,6 +316,13 @@ gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g,
 int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &prm, float *dgamma, float *dbeta,
                         cudaStream_t s);
 
+// gdn_tc_bwd2.cu: the TMA-fed, software-pipelined generation of this kernel (HW % 128 == 0 only)
+bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64_t C, int64_t HW);
+size_t gdn_tc_backward2_workspace(int64_t B, int64_t C, int64_t HW);
+int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
+                     int inverse, float *dx, float *dbeta, float *dgamma, void *workspace, size_t workspace_bytes,
+                     cudaStream_t s);
+
 static bool tcb_geometry(int64_t C, int *P, uint32_t *tmem_cols, size_t *smem) {
     if (C < 16 || C > 111) return false;
     *P = (int)((C + 1 + 15) / 16 * 16);
@@ -350,12 +365,16 @@ size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW) {
     uint32_t cols;
     size_t smem;
     if (!tcb_geometry(C, &P, &cols, &smem)) return 0;
-    return sizeof(float) * (size_t)tcb_grid(B * HW, cols, smem) * C * (C + 1) + 256;
+    const size_t v1 = sizeof(float) * (size_t)tcb_grid(B * HW, cols, smem) * C * (C + 1) + 256;
+    const size_t v2 = gdn_tc_backward2_workspace(B, C, HW);
+    return v1 > v2 ? v1 : v2;
 }
 
 int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
                     int inverse, float *dx, float *dbeta, float *dgamma, void *workspace, size_t workspace_bytes,
                     cudaStream_t s) {
+    if (gdn_tc_backward2_supported(x, g, B, C, HW))
+        return gdn_tc_backward2(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes, s);
     int P;
     uint32_t cols;
     size_t smem;

@@ -1,0 +1,561 @@
+// K4 backward, second generation: the three-contraction GDN / IGDN gradient of gdn_tc_bwd.cu, fed by TMA and
+// software-pipelined inside one persistent CTA per SM.
+//
+// What changed against gdn_tc_bwd.cu (same math, same 12 B/element):
+//   * x and g tiles arrive by cp.async.bulk.tensor (rank-3 map over the NCHW tensor, box = 32 pixels x C channels,
+//     128-byte swizzle).  A box lands as [channel][32 pixels] rows of 128 B in 1024-byte swizzle atoms, which IS the
+//     K-major (K = pixel) operand layout of the d gamma contraction: the threads square x / turn g into u IN PLACE, so
+//     the landing buffers double as the MMA3 operands and no second shared-memory copy exists.
+//   * NSTAGES landing stages are shared by NGROUPS compute groups of 256 threads; group q owns tiles q, q + NGROUPS, ...
+//     of the CTA's sequence and has its own TMEM accumulators (A/D and its own d gamma partial), its own MMA-issuing
+//     thread and its own mbarrier, so one group's epilogues overlap the other group's MMAs while the loads of the
+//     tiles after next are in flight.  The load of tile k + NSTAGES is issued by whichever group retires tile k's
+//     MMA3 (the last reader of that stage).
+//   * no global-load address arithmetic or load latency in the compute warps: registers hold x and g only.
+// Requires HW % 128 == 0 (a 128-pixel tile never straddles two images) and 16-byte aligned tensors; everything else
+// stays on gdn_tc_bwd.cu.
+#include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "gdn_params.cuh"
+#include "tc_ptx.cuh"
+
+namespace mmnc {
+
+namespace tcb2 {
+constexpr int TPG = 256;   // threads per compute group: thread t and t + 128 share a pixel and split the channels
+constexpr int TILE = 128;  // pixels per tile = TMEM lanes
+}  // namespace tcb2
+
+// Everything a compute group needs.  The kernel runs 512 threads per SM (128 registers each) and x / g of a tile
+// take 64 of them, so loop invariants must not sit in registers: the struct lives in SHARED memory and is read
+// through a volatile reference at the point of use (an LDS costs ~30 cycles; a spilled register comes back from L2
+// in ~340, because the L1 is a few KB once the shared-memory carve-out is at its maximum).  Descriptors, TMEM
+// columns and buffer addresses are derived from these few values where they are needed.
+struct Bwd2Ctx {
+    int C, R8, n_k;          // channels, 8-row groups per K atom, tiles of this CTA
+    int tiles_per_img;
+    uint32_t sb;             // channel stride in bytes
+    uint32_t stage0;         // shared address of stage 0 ([u | x2] per stage, R8 * 4096 bytes each)
+    uint32_t gamma0;         // shared address of the gamma tile; gamma^T follows P * P * 4 bytes later
+    uint32_t full_bar0, mma_bar0;  // shared addresses of the mbarrier arrays
+    uint32_t tmem_base;
+    const void *tm_x, *tm_g;
+    float *dx;
+};
+
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+
+template <int NSTAGES>
+__device__ __forceinline__ void bwd2_issue_tile(const volatile Bwd2Ctx &t, int k) {
+    const int s = k % NSTAGES;
+    const uint32_t tile = blockIdx.x + (uint32_t)k * gridDim.x;  // < 2^31 tiles (checked on the host)
+    const int b = (int)(tile / (uint32_t)t.tiles_per_img);
+    const int hw0 = (int)(tile - (uint32_t)b * (uint32_t)t.tiles_per_img) * tcb2::TILE;
+    const uint32_t bar = t.full_bar0 + 8u * (uint32_t)s;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)t.C * 1024u)
+                 : "memory");  // 2 tensors x 4 boxes x C rows x 128 B
+    const uint32_t R8 = (uint32_t)t.R8, buf_bytes = R8 * 4096u;
+    const uint32_t ub = t.stage0 + (uint32_t)s * 2u * buf_bytes, xb = ub + buf_bytes;
+    const uint64_t tmx = reinterpret_cast<uint64_t>(t.tm_x), tmg = reinterpret_cast<uint64_t>(t.tm_g);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const uint32_t o = (uint32_t)a * R8 * 1024u;
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(xb + o), "l"(tmx), "r"(hw0 + 32 * a), "r"(0), "r"(b), "r"(bar)
+            : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(ub + o), "l"(tmg), "r"(hw0 + 32 * a), "r"(0), "r"(b), "r"(bar)
+            : "memory");
+    }
+}
+
+// compile-time unrolled MMA chains (every per-step offset is an immediate inside the asm block, see tc_ptx.cuh)
+template <int KS, int NK>
+__device__ __forceinline__ void mma_ts_chain(uint32_t d, uint32_t a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if constexpr (KS < NK) {
+        tc::mma_tf32_ts_step<KS * 8, KS * 16>(d, a, b_lo, b_hi, idesc, KS > 0 ? 1u : 0u);
+        mma_ts_chain<KS + 1, NK>(d, a, b_lo, b_hi, idesc);
+    }
+}
+template <int KS>
+__device__ __forceinline__ void mma_ss_chain(uint32_t d3, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t atom16,
+                                             uint32_t idesc, uint32_t first_acc) {
+    if constexpr (KS < tcb2::TILE / 8) {
+        tc::mma_tf32_ss_step<(KS & 3) * 2>(d3, a_lo, b_lo, hi, (uint32_t)(KS >> 2) * atom16, idesc,
+                                           KS == 0 ? first_acc : 1u);
+        mma_ss_chain<KS + 1>(d3, a_lo, b_lo, hi, atom16, idesc, first_acc);
+    }
+}
+
+// One compute group's share of the CTA's tile sequence.  HALF (which half of the channels this thread owns) and
+// kInverse are template parameters so that channel indices are compile-time constants (immediate offsets).
+template <int KH8, int NGROUPS, int NSTAGES, int HALF, bool kInverse>
+__device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int group, int tg) {
+    using namespace tc;
+    using namespace tcb2;
+    constexpr int KH = KH8 * 8;   // channels handled by this thread
+    constexpr int P = KH * 2;     // padded channel count
+    constexpr int c_begin = HALF * KH;
+    constexpr int SAFE = P - 16;  // channels below this are always real (C > P - 16)
+    constexpr float coef = kInverse ? 0.5f : -0.5f;
+    // two groups = 128 registers per thread: g is then re-read from its landing buffer in epilogue 1 and f = g n^p
+    // is parked in spare TMEM columns until epilogue 2, so that only x stays in registers across the MMA waits
+    constexpr bool PARK = (NGROUPS == 2);
+    constexpr int KG = PARK ? 1 : KH;
+    constexpr uint32_t kcores = P >> 2;
+    constexpr uint32_t GAMMA_HI = desc_hi(kcores * 128u, 0);  // K-major, no swizzle: SBO = one 8-row group of cores
+    constexpr uint32_t PIX_HI = desc_hi(1024u, 2);            // K-major (K = pixel), 128-byte swizzle
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int C = t.C;
+    const int pix = tg & 127;
+    const bool leader = (tg == 0);
+    const uint32_t bar_id = 1u + (uint32_t)group;
+    const uint32_t tmem_base = t.tmem_base;
+    const uint32_t a_base = tmem_base + (uint32_t)(group * 2 * P);
+    const uint32_t lane_a = a_base + (((uint32_t)(((threadIdx.x >> 5) & 3) * 32)) << 16) + c_begin;
+    const uint32_t lane_d = lane_a + (uint32_t)P;
+    const uint32_t lane_f = lane_a + (uint32_t)((NGROUPS * 3 - group) * P);  // columns after every A / D / D3 region
+    const uint32_t mbar = t.mma_bar0 + 8u * (uint32_t)group;
+    // swizzled offset of (row c, pixel pix): rows of one 8-row group differ only in the XOR of address bits 4..6 with
+    // (c & 7), and every base below has zeros there, so   addr(c) = ((base | q << 4) ^ ((c & 7) << 4)) + row-group
+    // immediate : one register per buffer instead of eight precomputed offsets
+    uint32_t bq;
+    {
+        const int atomk = pix >> 5, p32 = pix & 31, R8 = t.R8;
+        bq = (uint32_t)(((atomk * R8 + (c_begin >> 3)) << 10) + ((p32 >> 2) << 4) + ((p32 & 3) << 2));
+    }
+    uint32_t parity = 0;
+    bool first = true;
+#pragma unroll 1
+    for (int k = group; k < t.n_k; k += NGROUPS) {
+        const int s = k % NSTAGES;
+        const uint32_t buf_bytes = (uint32_t)t.R8 * 4096u;
+        const uint32_t us = t.stage0 + (uint32_t)s * 2u * buf_bytes, xs = us + buf_bytes;
+        const uint32_t uq = us + bq, xq = xs + bq;
+        mbar_wait_addr(t.full_bar0 + 8u * (uint32_t)s, (uint32_t)((k / NSTAGES) & 1));
+        // ---- this thread's channels of x and g out of the landing buffers (conflict-free: a warp reads one 128 B row)
+        float xv[KH], gv[KG];
+#pragma unroll
+        for (int j = 0; j < KH; ++j) {
+            const int c = c_begin + j;
+            const bool real = (c < SAFE || c < C);
+            xv[j] = real ? ld_shared_f32((xq ^ (uint32_t)((j & 7) << 4)) + (uint32_t)(((j >> 3) << 10) + ((j & 7) << 7))) : 0.f;
+            if constexpr (!PARK)
+                gv[j] = real ? ld_shared_f32((uq ^ (uint32_t)((j & 7) << 4)) + (uint32_t)(((j >> 3) << 10) + ((j & 7) << 7))) : 0.f;
+        }
+        // ---- x^2 -> A (TMEM) and back into the landing buffer (MMA3's B operand); padded channel C is the constant 1,
+        //      whose shared-memory row was written once at start-up and is never touched by the TMA box (C rows)
+#pragma unroll
+        for (int j0 = 0; j0 < KH; j0 += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c_begin + j0 + j;
+                const uint32_t sq = to_tf32(xv[j0 + j] * xv[j0 + j]);
+                if (c < SAFE || c < C) {
+                    st_shared_u32((xq ^ (uint32_t)(j << 4)) + (uint32_t)((j0 << 7) + (j << 7)), sq);
+                    v[j] = sq;
+                } else {
+                    v[j] = (c == C) ? 0x3f800000u : 0u;
+                }
+            }
+            tmem_st8(lane_a + j0, v);
+        }
+        tmem_st_wait();
+        fence_async_smem();
+        fence_before();
+        named_bar_sync(bar_id, TPG);
+        // ---- MMA1: D = x2 * gamma^T (+ beta through the constant column)
+        if (leader) {
+            fence_after();
+            mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0, 128), GAMMA_HI, IDESC);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+        }
+        mbar_wait_addr(mbar, parity);
+        parity ^= 1;
+        fence_after();
+        // ---- epilogue 1: u -> A (TMEM) and over g in the landing buffer (MMA3's A operand); f = g n^p kept for later
+#pragma unroll
+        for (int j0 = 0; j0 < KH; j0 += 8) {
+            uint32_t r[8], uu[8], ff[8];
+            float g8[8];
+            tmem_ld8(lane_d + j0, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c_begin + j0 + j;
+                if constexpr (PARK)
+                    g8[j] = (c < SAFE || c < C) ? ld_shared_f32((uq ^ (uint32_t)(j << 4)) + (uint32_t)((j0 << 7) + (j << 7))) : 0.f;
+                else
+                    g8[j] = gv[(j0 + j) % KG];
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c_begin + j0 + j;
+                const float n = __uint_as_float(r[j]);
+                const float rs = fast_rsqrt(n);
+                const float pw = kInverse ? n * rs : rs;         // n^p
+                const float pm1 = kInverse ? rs : rs * rs * rs;  // n^(p-1)
+                const float u = (coef * g8[j]) * (xv[j0 + j] * pm1);
+                const float f = g8[j] * pw;
+                if constexpr (PARK) ff[j] = __float_as_uint(f); else gv[(j0 + j) % KG] = f;
+                if (c < SAFE || c < C) {
+                    uu[j] = to_tf32(u);
+                    st_shared_u32((uq ^ (uint32_t)(j << 4)) + (uint32_t)((j0 << 7) + (j << 7)), uu[j]);
+                } else {
+                    uu[j] = 0u;
+                }
+            }
+            tmem_st8(lane_a + j0, uu);
+            if constexpr (PARK) tmem_st8(lane_f + j0, ff);
+        }
+        tmem_st_wait();
+        fence_async_smem();
+        fence_before();
+        named_bar_sync(bar_id, TPG);
+        // ---- MMA2: D = u * gamma (B = gamma^T tile);  MMA3: D3 += u^T x2 (K = 128 pixels of this stage)
+        if (leader) {
+            fence_after();
+            mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0 + (uint32_t)(P * P * 4), 128), GAMMA_HI, IDESC);
+            mma_ss_chain<0>(tmem_base + (uint32_t)(NGROUPS * 2 * P + group * P), desc_lo(us, 16), desc_lo(xs, 16), PIX_HI,
+                            (uint32_t)t.R8 * 64u, IDESC, first ? 0u : 1u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+        }
+        mbar_wait_addr(mbar, parity);
+        parity ^= 1;
+        fence_after();
+        // the stage is free (MMA3 was its last reader): refill it with the tile NSTAGES ahead
+        if (leader && k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
+        // ---- epilogue 2: dx = g n^p + 2 x t
+        {
+            const uint32_t tile = blockIdx.x + (uint32_t)k * gridDim.x;
+            const uint32_t tpi = (uint32_t)t.tiles_per_img, sb = t.sb;
+            const uint32_t b = tile / tpi;
+            const uint32_t hw0 = (tile - b * tpi) * TILE;
+            float *dxb = t.dx + ((int64_t)(b * (uint32_t)C) * (int64_t)(sb >> 2) + hw0 + pix);
+#pragma unroll
+            for (int j0 = 0; j0 < KH; j0 += 8) {
+                uint32_t r[8], ff[8];
+                tmem_ld8(lane_d + j0, r);
+                if constexpr (PARK) tmem_ld8(lane_f + j0, ff);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c_begin + j0 + j;
+                    const float f = PARK ? __uint_as_float(ff[j]) : gv[(j0 + j) % KG];
+                    const float out = fmaf(2.f * xv[j0 + j], __uint_as_float(r[j]), f);
+                    if (c < SAFE || c < C) __stcs(chan_ptr(dxb, sb, c), out);
+                }
+            }
+        }
+        fence_before();
+        named_bar_sync(bar_id, TPG);  // A and D of this group are free again
+        fence_after();
+        first = false;
+    }
+    return first;
+}
+
+template <int KH8, int NGROUPS, int NSTAGES, bool kInverse>
+__global__ void __launch_bounds__(NGROUPS *tcb2::TPG, 1)
+gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
+                        int ntiles, int tiles_per_img, int HW, const GdnParams prm, float *__restrict__ dx,
+                        float *__restrict__ part, int C, uint32_t tmem_cols) {
+    using namespace tc;
+    using namespace tcb2;
+    constexpr int P = KH8 * 16;
+    constexpr int THREADS = NGROUPS * TPG;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[NSTAGES];
+    __shared__ uint64_t mma_bar[NGROUPS];
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int R8 = (C + 1 + 7) >> 3;
+    const uint32_t buf_bytes = (uint32_t)R8 * 4096u;  // 4 K atoms of 32 pixels, R8 swizzle atoms of 8 rows each
+    const uint32_t stage_bytes = 2u * buf_bytes;      // [u | x2]
+    float *Bs = reinterpret_cast<float *>(smem + (size_t)NSTAGES * stage_bytes);  // gamma   (N = i, K = j)
+    float *Bs2 = Bs + P * P;                                                        // gamma^T (N = k, K = i)
+    const int warp = threadIdx.x >> 5;
+    const int group = threadIdx.x / TPG, tg = threadIdx.x % TPG;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int q = 0; q < NGROUPS; ++q) mbar_init(&mma_bar[q], 1);
+        tma_prefetch_desc(&tm_x);
+        tma_prefetch_desc(&tm_g);
+    }
+    // gamma tiles, as in gdn_tc_bwd.cu: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]); column k = C holds beta
+    constexpr int kcores = P >> 2;
+    for (int idx = threadIdx.x; idx < P * P; idx += THREADS) {
+        const int n = idx / P, k = idx - n * P;
+        float v = 0.f;
+        if (n < C && k < C) v = prm.g((int64_t)n * C + k);
+        else if (n < C && k == C) v = prm.b(n);
+        else if (n >= C && k == C) v = 1.f;  // padded outputs get norm = 1 (finite)
+        const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
+        reinterpret_cast<uint32_t *>(Bs)[off] = to_tf32(v);
+        const float vt = (n < C && k < C) ? prm.g((int64_t)k * C + n) : 0.f;
+        reinterpret_cast<uint32_t *>(Bs2)[off] = to_tf32(vt);
+    }
+    // landing stages: rows the TMA box never writes (r >= C) are 0, except row C of every x2 buffer = the constant 1
+    {
+        const uint32_t words_per_buf = buf_bytes >> 2, words = (uint32_t)NSTAGES * 2u * words_per_buf;
+        const uint32_t atom_words = (uint32_t)R8 * 256u;
+        for (uint32_t i = threadIdx.x; i < words; i += THREADS) {
+            const uint32_t buf = i / words_per_buf, o = i - buf * words_per_buf;
+            const uint32_t oa = o % atom_words;
+            const int r = (int)((oa >> 8) << 3) + (int)((oa >> 5) & 7);  // 1024 B per 8-row group, 128 B per row
+            reinterpret_cast<uint32_t *>(smem)[i] = ((buf & 1u) && r == C) ? 0x3f800000u : 0u;
+        }
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+
+    __shared__ Bwd2Ctx ctx_s;
+    if (threadIdx.x == 0) {
+    Bwd2Ctx ctx;
+    ctx.C = C; ctx.R8 = R8;
+    ctx.tiles_per_img = tiles_per_img;
+    ctx.n_k = (blockIdx.x < (uint32_t)ntiles) ? (int)(((uint32_t)ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    ctx.sb = (uint32_t)HW * 4u;
+    ctx.stage0 = smem_u32(smem);
+    ctx.gamma0 = smem_u32(Bs);
+    ctx.full_bar0 = smem_u32(&full_bar[0]);
+    ctx.mma_bar0 = smem_u32(&mma_bar[0]);
+    ctx.tmem_base = tmem_base_s;
+    ctx.tm_x = &tm_x; ctx.tm_g = &tm_g;
+    ctx.dx = dx;
+    ctx_s = ctx;
+    }
+    __syncthreads();
+    const volatile Bwd2Ctx &ctx = ctx_s;
+    if (threadIdx.x == 0) {
+        const int n_k = ctx.n_k;
+        const int pre = n_k < NSTAGES ? n_k : NSTAGES;
+        for (int k = 0; k < pre; ++k) bwd2_issue_tile<NSTAGES>(ctx, k);
+    }
+    const bool first = ((tg >> 7) == 0) ? bwd2_group_loop<KH8, NGROUPS, NSTAGES, 0, kInverse>(ctx, group, tg)
+                                        : bwd2_group_loop<KH8, NGROUPS, NSTAGES, 1, kInverse>(ctx, group, tg);
+    // ---- this group's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
+    float *dst = part + ((int64_t)blockIdx.x * NGROUPS + group) * C * (C + 1);
+    const int pix = tg & 127;
+    if ((tg >> 7) == 0) {
+        if (!first) {
+            const uint32_t lane_d3 = tmem_base_s + (((uint32_t)((warp & 3) * 32)) << 16) +
+                                     (uint32_t)(NGROUPS * 2 * P + group * P);
+#pragma unroll 1
+            for (int j0 = 0; j0 < P; j0 += 8) {
+                uint32_t r[8];
+                tmem_ld8(lane_d3 + j0, r);
+                tmem_ld_wait();
+                if (pix < C) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j0 + j <= C) dst[(int64_t)pix * (C + 1) + j0 + j] = __uint_as_float(r[j]);
+                }
+            }
+        } else if (pix < C) {
+            for (int j = 0; j <= C; ++j) dst[(int64_t)pix * (C + 1) + j] = 0.f;  // group without tiles
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, tmem_cols);
+}
+
+// fixed-order reduction of per-group partials [ksplit][C][C+1] -> d gamma, d beta (gdn_simt.cu)
+int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &prm, float *dgamma, float *dbeta,
+                        cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+struct Bwd2Geometry {
+    int P, groups, stages;
+    uint32_t tmem_cols;
+    size_t smem;
+};
+
+static bool bwd2_geometry(int64_t C, Bwd2Geometry *g) {
+    if (C < 16 || C > 111) return false;
+    const int P = (int)((C + 1 + 15) / 16 * 16);
+    const size_t R8 = (size_t)(C + 1 + 7) / 8;
+    const size_t stage = 2 * R8 * 4096, gam = 2 * (size_t)P * P * 4;
+    const size_t budget = 227 * 1024 - 1024 - 256;  // alignment slack + static shared memory
+    // two groups need x and g of a tile in 128 registers per thread: P <= 64 (32 channels per thread)
+    int groups = (P <= 64) ? 2 : 1;
+    int stages = 0;
+    for (;;) {
+        const int want = (groups == 2) ? 3 : 2;
+        for (int s = want; s >= groups; --s)
+            if ((size_t)s * stage + gam <= budget) { stages = s; break; }
+        if (stages || groups == 1) break;
+        groups = 1;
+    }
+    if (!stages) {
+        if (stage + gam > budget) return false;
+        stages = 1;
+    }
+    g->P = P; g->groups = groups; g->stages = stages;
+    const int need = groups * (groups == 2 ? 4 : 3) * P;  // A, D, D3 per group (+ the parked f when two groups share the SM)
+    uint32_t cols = 32;
+    while ((int)cols < need) cols <<= 1;
+    if (cols > 512) return false;
+    g->tmem_cols = cols;
+    // MMA3 views 128 rows (A) / P rows (B) of buffers that store 8 R8 rows per K atom: the over-read of the last K
+    // atom of the last stage must stay inside the allocation (gamma follows the stages; pad if that is not enough)
+    size_t bytes = (size_t)stages * stage + gam;
+    const size_t last_u = (size_t)(stages - 1) * stage, last_x = last_u + R8 * 4096;
+    const size_t over_a = last_u + (3 * R8 + 16) * 1024, over_b = last_x + (3 * R8 + (size_t)P / 8) * 1024;
+    if (bytes < over_a) bytes = over_a;
+    if (bytes < over_b) bytes = over_b;
+    g->smem = bytes + 1024;
+    return g->smem + 256 <= 227 * 1024;
+}
+
+static int bwd2_mode() {  // MMNC_GDN_BWD = v1 | v2 | auto (default)
+    static int mode = []() {
+        const char *e = getenv("MMNC_GDN_BWD");
+        if (e && !strcmp(e, "v1")) return 1;
+        if (e && !strcmp(e, "v2")) return 2;
+        return 0;
+    }();
+    return mode;
+}
+
+bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64_t C, int64_t HW) {
+    Bwd2Geometry geo;
+    if (bwd2_mode() == 1) return false;
+    if (!bwd2_geometry(C, &geo)) return false;
+    if (HW % tcb2::TILE != 0 || HW >= (1 << 24) || B >= (1 << 24) || B * HW / tcb2::TILE >= (1ll << 31) ||
+        B * C >= (1ll << 31))
+        return false;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(g) & 15)) return false;
+    if (B * HW / tcb2::TILE < 2 * (int64_t)sm_count() && bwd2_mode() != 2) return false;  // too few tiles to pipeline
+    return encode_tiled() != nullptr;
+}
+
+size_t gdn_tc_backward2_workspace(int64_t B, int64_t C, int64_t HW) {
+    Bwd2Geometry geo;
+    if (!bwd2_geometry(C, &geo)) return 0;
+    (void)B; (void)HW;
+    return sizeof(float) * (size_t)sm_count() * geo.groups * C * (C + 1) + 256;
+}
+
+// cuTensorMapEncodeTiled is a driver-API call and wants a current context on the calling thread.  Runtime-API-only
+// threads (torch's autograd worker on device 0 never calls cudaSetDevice) may not have one bound yet.
+static void bind_primary_context() {
+    typedef CUresult (*GetCurrentFn)(CUcontext *);
+    static GetCurrentFn get_current = []() -> GetCurrentFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<GetCurrentFn>(p);
+    }();
+    CUcontext cur = nullptr;
+    if (get_current && get_current(&cur) == CUDA_SUCCESS && cur != nullptr) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);  // CUDA 12: initialises and binds the primary context
+    cudaGetLastError();
+}
+
+static int make_map(CUtensorMap *m, const float *p, int64_t B, int64_t C, int64_t HW) {
+    const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)C * HW * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)C, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(p), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gdn_tc_backward2: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return MMNC_ERR_CUDA;
+    }
+    return MMNC_OK;
+}
+
+int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
+                     int inverse, float *dx, float *dbeta, float *dgamma, void *workspace, size_t workspace_bytes,
+                     cudaStream_t s) {
+    Bwd2Geometry geo;
+    if (!bwd2_geometry(C, &geo)) {
+        set_error("gdn_tc_backward2: C = %lld not supported", (long long)C);
+        return MMNC_ERR_UNSUPPORTED;
+    }
+    const int64_t ntiles = B * HW / tcb2::TILE;
+    int64_t grid = sm_count();
+    if (grid > ntiles) grid = ntiles;
+    const int ksplit = (int)grid * geo.groups;
+    MMNC_REQUIRE(workspace_bytes >= sizeof(float) * (size_t)ksplit * C * (C + 1), "gdn_backward: workspace too small");
+    CUtensorMap tm_x, tm_g;
+    bind_primary_context();
+    if (int rc = make_map(&tm_x, x, B, C, HW)) return rc;
+    if (int rc = make_map(&tm_g, g, B, C, HW)) return rc;
+    using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, int, const GdnParams, float *, float *,
+                            int, uint32_t);
+    Kernel kernel = nullptr;
+#define MMNC_PICK(N, G, S) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, true> : (Kernel)gdn_tc_backward2_kernel<N, G, S, false>)
+    const int key = (geo.P / 16) * 100 + geo.groups * 10 + geo.stages;
+    switch (key) {
+        case 223: kernel = MMNC_PICK(2, 2, 3); break;
+        case 323: kernel = MMNC_PICK(3, 2, 3); break;
+        case 423: kernel = MMNC_PICK(4, 2, 3); break;
+        case 512: kernel = MMNC_PICK(5, 1, 2); break;
+        case 611: kernel = MMNC_PICK(6, 1, 1); break;
+        case 711: kernel = MMNC_PICK(7, 1, 1); break;
+        default: break;
+    }
+#undef MMNC_PICK
+    if (kernel == nullptr) {
+        set_error("gdn_tc_backward2: no kernel instance for C = %lld (P %d, groups %d, stages %d)", (long long)C, geo.P,
+                  geo.groups, geo.stages);
+        return MMNC_ERR_UNSUPPORTED;
+    }
+    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
+    float *part = static_cast<float *>(workspace);
+    kernel<<<(unsigned)grid, geo.groups * tcb2::TPG, geo.smem, s>>>(tm_x, tm_g, (int)ntiles, (int)(HW / tcb2::TILE), (int)HW,
+                                                                   prm, dx, part, (int)C, geo.tmem_cols);
+    if (int rc = after_launch("gdn_tc_backward2_kernel")) return rc;
+    return gdn_reduce_partials(part, ksplit, (int)C, prm, dgamma, dbeta, s);
+}
+
+}  // namespace mmnc

@@ -144,5 +144,73 @@ __device__ __forceinline__ uint32_t make_idesc_ex(int n, bool a_mn, bool b_mn) {
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+
+// ---- TMA (cp.async.bulk.tensor) and friends -------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one box of a rank-3 tensor map -> shared memory; completion is counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void *tmap, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// named barrier over a subset of the CTA (id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+
+// ---- MMA issue with the shared-memory descriptors assembled INSIDE the asm block ---------------------------------
+// A descriptor differs from step to step only in its 14-bit address field.  Building {lo + step, hi} inside a volatile
+// asm keeps ptxas from hoisting a dozen loop-invariant 64-bit descriptors out of the tile loop and spilling them:
+// with the shared-memory carve-out at its maximum the L1 is a few KB, a spilled descriptor comes back from L2
+// (~340 cycles per LDL, measured with ncu), and the single MMA-issuing thread serialises those.
+template <int A_COL_STEP, int B_STEP16>
+__device__ __forceinline__ void mma_tf32_ts_step(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 ta, lo;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "add.u32 ta, %1, %6;\n\t"
+        "add.u32 lo, %2, %7;\n\t"
+        "mov.b64 db, {lo, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [ta], db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "n"(A_COL_STEP), "n"(B_STEP16)
+        : "memory");
+}
+// both operands in shared memory; `off16` is a run-time offset (in 16-byte units) added to both address fields
+template <int STEP16>
+__device__ __forceinline__ void mma_tf32_ss_step(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                 uint32_t off16, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 la, lb;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "add.u32 la, %1, %4;\n\t"
+        "add.u32 lb, %2, %4;\n\t"
+        "add.u32 la, la, %7;\n\t"
+        "add.u32 lb, lb, %7;\n\t"
+        "mov.b64 da, {la, %3};\n\t"
+        "mov.b64 db, {lb, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(off16), "r"(idesc), "r"(accumulate), "n"(STEP16)
+        : "memory");
+}
+// the two 32-bit halves of make_desc()
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+
 }  // namespace tc
 }  // namespace mmnc

@@ -358,6 +358,67 @@ def test_gdn_backward_tensor_core(shape, inverse):
     assert close(ours.gamma.grad, refd.gamma.grad, 2e-3)
 
 
+
+def _gdn_bwd_variant(x, g, precision="tf32"):
+    B, C = x.shape[:2]
+    HW = x.numel() // (B * C)
+    return int(mm._lib.lib().mmnc_gdn_backward_variant(x.data_ptr(), g.data_ptr(), B, C, HW,
+                                                        mm.ops.GDN_PRECISION[precision]))
+
+
+# (P, groups, stages) instances of gdn_tc_bwd2.cu: C=20 -> (32,2,3), 40 -> (48,2,3), 50 / 63 -> (64,2,3), 64 -> (80,2,2),
+# 90 -> (96,1,1), 100 / 110 -> (112,1,1); 320-640 tiles on 148 CTAs: groups with 1, 2 and 0 tiles all occur
+@pytest.mark.parametrize("shape", [(10, 50, 64, 64), (5, 100, 128, 64), (10, 64, 64, 64), (12, 20, 64, 64),
+                                   (10, 40, 32, 128), (10, 90, 64, 64), (10, 63, 64, 64), (10, 110, 64, 64),
+                                   (20, 16, 16, 128)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_backward_tensor_core_pipelined(shape, inverse):
+    """TMA-fed, software-pipelined tcgen05 backward (gdn_tc_bwd2.cu) against the float64 oracle; same stated
+    tolerance as the first-generation fused kernel (2e-3 of the largest entry)."""
+    torch.manual_seed(17)
+    C = shape[1]
+    ours, ref = _pair_gdn(C, inverse, precision="tf32")
+    refd = R.GDN(C, inverse=inverse).double()
+    refd.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
+    x, g = torch.randn(*shape), torch.randn(*shape)
+    xd, gd = x.to(DEV).requires_grad_(True), g.to(DEV)
+    assert _gdn_bwd_variant(xd, gd) == 3, "shape should take the pipelined kernel"
+    before = mm.launch_count()
+    ours(xd).backward(gd)
+    torch.cuda.synchronize()
+    assert mm.launch_count() - before == 1 + 2
+    x64 = x.double().requires_grad_(True)
+    refd(x64).backward(g.double())
+
+    def close(a, b, tol):
+        return ((a.cpu().double() - b).abs().max() / b.abs().max()).item() <= tol
+
+    assert close(xd.grad, x64.grad, 2e-3), ((xd.grad.cpu().double() - x64.grad).abs().max(), x64.grad.abs().max())
+    assert close(ours.beta.grad, refd.beta.grad, 2e-3)
+    assert close(ours.gamma.grad, refd.gamma.grad, 2e-3)
+
+
+@pytest.mark.parametrize("shape", [(32, 50, 128, 128), (16, 100, 128, 128), (24, 64, 128, 128)])
+def test_gdn_backward_pipelined_long_sequences(shape):
+    """Dozens of tiles per CTA (every stage and mbarrier phase wraps many times): the pipelined kernel against the
+    fp32 SIMT kernel on the same device, and bit-identical results run to run (fixed-order partial reduction)."""
+    torch.manual_seed(18)
+    C = shape[1]
+    ours, _ = _pair_gdn(C, False, precision="tf32")
+    x = torch.randn(*shape, device=DEV)
+    g = torch.randn(*shape, device=DEV)
+    assert _gdn_bwd_variant(x, g) == 3
+    beta, gamma = ours.beta_reparam(ours.beta).detach(), ours.gamma_reparam(ours.gamma).detach()
+    outs = []
+    for prec in ("tf32", "tf32", "fp32"):
+        xr, br, gr = x.clone().requires_grad_(True), beta.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
+        outs.append(torch.autograd.grad(mm.ops.gdn(xr, br, gr, False, prec), [xr, br, gr], g))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b), "pipelined backward is not deterministic"
+    for a, b in zip(outs[0], outs[2]):
+        assert ((a - b).abs().max() / b.abs().max()).item() <= 2e-3
+
+
 def test_gdn_reparam_lower_bound_gradient():
     """A.2 / A.5: below the bound the gradient passes only if it is negative."""
     C = 4
