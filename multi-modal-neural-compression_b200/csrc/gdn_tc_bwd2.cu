@@ -103,35 +103,51 @@ __device__ __forceinline__ void mma_ss_chain(uint32_t d3, uint32_t a_lo, uint32_
     }
 }
 
-// One compute group's share of the CTA's tile sequence.  HALF (which half of the channels this thread owns) and
-// kInverse are template parameters so that channel indices are compile-time constants (immediate offsets).
-template <int KH8, int NGROUPS, int NSTAGES, int HALF, bool kInverse>
+// tcgen05.ld / st of W = 8 or 16 consecutive columns
+template <int W>
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&r)[W]) {
+    if constexpr (W == 16) tc::tmem_ld16(taddr, r); else tc::tmem_ld8(taddr, r);
+}
+template <int W>
+__device__ __forceinline__ void tmem_stw(uint32_t taddr, const uint32_t (&r)[W]) {
+    if constexpr (W == 16) tc::tmem_st16(taddr, r); else tc::tmem_st8(taddr, r);
+}
+
+// One compute group's share of the CTA's tile sequence.  Thread (pix, half) owns channels [half KH, half KH + KH) of
+// pixel pix.  `half` is a run-time value on purpose: one copy of the (fully unrolled) tile body instead of two keeps
+// the instruction footprint inside the instruction cache (ncu: 21 % of the stalls were instruction fetches with two
+// copies).  Channel offsets are folded into the per-thread TMEM / shared / global bases; only the last 16 channels of
+// a thread can be padding, and a 16-bit mask says which.
+template <int KH8, int NGROUPS, int NSTAGES, bool kInverse>
 __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int group, int tg) {
     using namespace tc;
     using namespace tcb2;
     constexpr int KH = KH8 * 8;   // channels handled by this thread
     constexpr int P = KH * 2;     // padded channel count
-    constexpr int c_begin = HALF * KH;
-    constexpr int SAFE = P - 16;  // channels below this are always real (C > P - 16)
+    constexpr int TAIL0 = (KH > 16) ? KH - 16 : 0;  // first local channel that may be padding (C > P - 16)
     constexpr float coef = kInverse ? 0.5f : -0.5f;
     // two groups = 128 registers per thread: g is then re-read from its landing buffer in epilogue 1 and f = g n^p
     // is parked in spare TMEM columns until epilogue 2, so that only x stays in registers across the MMA waits
     constexpr bool PARK = (NGROUPS == 2);
     constexpr int KG = PARK ? 1 : KH;
+    constexpr int W = (KH % 16 == 0 && !PARK) ? 16 : 8;  // columns per tcgen05.ld / st
+    constexpr int W1 = PARK ? 8 : W;            // epilogue 1 is where the 128-register budget is tightest
     constexpr uint32_t kcores = P >> 2;
     constexpr uint32_t GAMMA_HI = desc_hi(kcores * 128u, 0);  // K-major, no swizzle: SBO = one 8-row group of cores
     constexpr uint32_t PIX_HI = desc_hi(1024u, 2);            // K-major (K = pixel), 128-byte swizzle
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int C = t.C;
     const int pix = tg & 127;
+    const int c_begin = (tg >> 7) * KH;
     const bool leader = (tg == 0);
     const uint32_t bar_id = 1u + (uint32_t)group;
     const uint32_t tmem_base = t.tmem_base;
     const uint32_t a_base = tmem_base + (uint32_t)(group * 2 * P);
-    const uint32_t lane_a = a_base + (((uint32_t)(((threadIdx.x >> 5) & 3) * 32)) << 16) + c_begin;
+    const uint32_t lane_a = a_base + (((uint32_t)(((threadIdx.x >> 5) & 3) * 32)) << 16) + (uint32_t)c_begin;
     const uint32_t lane_d = lane_a + (uint32_t)P;
     const uint32_t lane_f = lane_a + (uint32_t)((NGROUPS * 3 - group) * P);  // columns after every A / D / D3 region
     const uint32_t mbar = t.mma_bar0 + 8u * (uint32_t)group;
+    // local channels TAIL0 + i with i < one_i are real, i == one_i is the constant-1 channel C, the rest is padding
+    const int one_i = t.C - c_begin - TAIL0;
     // swizzled offset of (row c, pixel pix): rows of one 8-row group differ only in the XOR of address bits 4..6 with
     // (c & 7), and every base below has zeros there, so   addr(c) = ((base | q << 4) ^ ((c & 7) << 4)) + row-group
     // immediate : one register per buffer instead of eight precomputed offsets
@@ -140,8 +156,14 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         const int atomk = pix >> 5, p32 = pix & 31, R8 = t.R8;
         bq = (uint32_t)(((atomk * R8 + (c_begin >> 3)) << 10) + ((p32 >> 2) << 4) + ((p32 & 3) << 2));
     }
+    // `oi` is one_i laundered through an empty asm before every phase: otherwise ptxas hoists the sixteen padding
+    // selects out of the tile loop, keeps them in registers for the whole kernel and spills them
+#define MMNC_REAL(j) ((j) < TAIL0 || (j) - TAIL0 < oi)
+#define MMNC_FRESH_OI() asm volatile("" : "+r"(oi))
+#define MMNC_SOFF(base, j) (((base) ^ (uint32_t)(((j) & 7) << 4)) + (uint32_t)((((j) >> 3) << 10) + (((j) & 7) << 7)))
     uint32_t parity = 0;
     bool first = true;
+    int oi = one_i;
 #pragma unroll 1
     for (int k = group; k < t.n_k; k += NGROUPS) {
         const int s = k % NSTAGES;
@@ -149,33 +171,31 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         const uint32_t us = t.stage0 + (uint32_t)s * 2u * buf_bytes, xs = us + buf_bytes;
         const uint32_t uq = us + bq, xq = xs + bq;
         mbar_wait_addr(t.full_bar0 + 8u * (uint32_t)s, (uint32_t)((k / NSTAGES) & 1));
-        // ---- this thread's channels of x and g out of the landing buffers (conflict-free: a warp reads one 128 B row)
+        // ---- this thread's channels of x (and g) out of the landing buffers (conflict-free: a warp reads one 128 B row)
         float xv[KH], gv[KG];
+        MMNC_FRESH_OI();
 #pragma unroll
         for (int j = 0; j < KH; ++j) {
-            const int c = c_begin + j;
-            const bool real = (c < SAFE || c < C);
-            xv[j] = real ? ld_shared_f32((xq ^ (uint32_t)((j & 7) << 4)) + (uint32_t)(((j >> 3) << 10) + ((j & 7) << 7))) : 0.f;
-            if constexpr (!PARK)
-                gv[j] = real ? ld_shared_f32((uq ^ (uint32_t)((j & 7) << 4)) + (uint32_t)(((j >> 3) << 10) + ((j & 7) << 7))) : 0.f;
+            const bool real = MMNC_REAL(j);
+            xv[j] = real ? ld_shared_f32(MMNC_SOFF(xq, j)) : 0.f;
+            if constexpr (!PARK) gv[j] = real ? ld_shared_f32(MMNC_SOFF(uq, j)) : 0.f;
         }
         // ---- x^2 -> A (TMEM) and back into the landing buffer (MMA3's B operand); padded channel C is the constant 1,
         //      whose shared-memory row was written once at start-up and is never touched by the TMA box (C rows)
 #pragma unroll
-        for (int j0 = 0; j0 < KH; j0 += 8) {
-            uint32_t v[8];
+        for (int j0 = 0; j0 < KH; j0 += W) {
+            uint32_t v[W];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = c_begin + j0 + j;
-                const uint32_t sq = to_tf32(xv[j0 + j] * xv[j0 + j]);
-                if (c < SAFE || c < C) {
-                    st_shared_u32((xq ^ (uint32_t)(j << 4)) + (uint32_t)((j0 << 7) + (j << 7)), sq);
+            for (int j = 0; j < W; ++j) {
+                const uint32_t sq = to_tf32_fast(xv[j0 + j] * xv[j0 + j]);
+                if (MMNC_REAL(j0 + j)) {
+                    st_shared_u32(MMNC_SOFF(xq, j0 + j), sq);
                     v[j] = sq;
                 } else {
-                    v[j] = (c == C) ? 0x3f800000u : 0u;
+                    v[j] = (j0 + j - TAIL0 == oi) ? 0x3f800000u : 0u;
                 }
             }
-            tmem_st8(lane_a + j0, v);
+            tmem_stw<W>(lane_a + j0, v);
         }
         tmem_st_wait();
         fence_async_smem();
@@ -191,23 +211,22 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         parity ^= 1;
         fence_after();
         // ---- epilogue 1: u -> A (TMEM) and over g in the landing buffer (MMA3's A operand); f = g n^p kept for later
+        MMNC_FRESH_OI();
 #pragma unroll
-        for (int j0 = 0; j0 < KH; j0 += 8) {
-            uint32_t r[8], uu[8], ff[8];
-            float g8[8];
-            tmem_ld8(lane_d + j0, r);
+        for (int j0 = 0; j0 < KH; j0 += W1) {
+            uint32_t r[W1], uu[W1], ff[W1];
+            float g8[W1];
+            tmem_ldw<W1>(lane_d + j0, r);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = c_begin + j0 + j;
+            for (int j = 0; j < W1; ++j) {
                 if constexpr (PARK)
-                    g8[j] = (c < SAFE || c < C) ? ld_shared_f32((uq ^ (uint32_t)(j << 4)) + (uint32_t)((j0 << 7) + (j << 7))) : 0.f;
+                    g8[j] = MMNC_REAL(j0 + j) ? ld_shared_f32(MMNC_SOFF(uq, j0 + j)) : 0.f;
                 else
                     g8[j] = gv[(j0 + j) % KG];
             }
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = c_begin + j0 + j;
+            for (int j = 0; j < W1; ++j) {
                 const float n = __uint_as_float(r[j]);
                 const float rs = fast_rsqrt(n);
                 const float pw = kInverse ? n * rs : rs;         // n^p
@@ -215,15 +234,15 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                 const float u = (coef * g8[j]) * (xv[j0 + j] * pm1);
                 const float f = g8[j] * pw;
                 if constexpr (PARK) ff[j] = __float_as_uint(f); else gv[(j0 + j) % KG] = f;
-                if (c < SAFE || c < C) {
-                    uu[j] = to_tf32(u);
-                    st_shared_u32((uq ^ (uint32_t)(j << 4)) + (uint32_t)((j0 << 7) + (j << 7)), uu[j]);
+                if (MMNC_REAL(j0 + j)) {
+                    uu[j] = to_tf32_fast(u);
+                    st_shared_u32(MMNC_SOFF(uq, j0 + j), uu[j]);
                 } else {
                     uu[j] = 0u;
                 }
             }
-            tmem_st8(lane_a + j0, uu);
-            if constexpr (PARK) tmem_st8(lane_f + j0, ff);
+            tmem_stw<W1>(lane_a + j0, uu);
+            if constexpr (PARK) tmem_stw<W1>(lane_f + j0, ff);
         }
         tmem_st_wait();
         fence_async_smem();
@@ -248,19 +267,19 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
             const uint32_t tpi = (uint32_t)t.tiles_per_img, sb = t.sb;
             const uint32_t b = tile / tpi;
             const uint32_t hw0 = (tile - b * tpi) * TILE;
-            float *dxb = t.dx + ((int64_t)(b * (uint32_t)C) * (int64_t)(sb >> 2) + hw0 + pix);
+            MMNC_FRESH_OI();
+            float *dxb = t.dx + ((int64_t)(b * (uint32_t)t.C + (uint32_t)c_begin) * (int64_t)(sb >> 2) + hw0 + pix);
 #pragma unroll
-            for (int j0 = 0; j0 < KH; j0 += 8) {
-                uint32_t r[8], ff[8];
-                tmem_ld8(lane_d + j0, r);
-                if constexpr (PARK) tmem_ld8(lane_f + j0, ff);
+            for (int j0 = 0; j0 < KH; j0 += W) {
+                uint32_t r[W], ff[W];
+                tmem_ldw<W>(lane_d + j0, r);
+                if constexpr (PARK) tmem_ldw<W>(lane_f + j0, ff);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = c_begin + j0 + j;
+                for (int j = 0; j < W; ++j) {
                     const float f = PARK ? __uint_as_float(ff[j]) : gv[(j0 + j) % KG];
                     const float out = fmaf(2.f * xv[j0 + j], __uint_as_float(r[j]), f);
-                    if (c < SAFE || c < C) __stcs(chan_ptr(dxb, sb, c), out);
+                    if (MMNC_REAL(j0 + j)) __stcs(chan_ptr(dxb, sb, j0 + j), out);
                 }
             }
         }
@@ -269,6 +288,9 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         fence_after();
         first = false;
     }
+#undef MMNC_REAL
+#undef MMNC_FRESH_OI
+#undef MMNC_SOFF
     return first;
 }
 
@@ -353,8 +375,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const int pre = n_k < NSTAGES ? n_k : NSTAGES;
         for (int k = 0; k < pre; ++k) bwd2_issue_tile<NSTAGES>(ctx, k);
     }
-    const bool first = ((tg >> 7) == 0) ? bwd2_group_loop<KH8, NGROUPS, NSTAGES, 0, kInverse>(ctx, group, tg)
-                                        : bwd2_group_loop<KH8, NGROUPS, NSTAGES, 1, kInverse>(ctx, group, tg);
+    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, kInverse>(ctx, group, tg);
     // ---- this group's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
     float *dst = part + ((int64_t)blockIdx.x * NGROUPS + group) * C * (C + 1);
     const int pix = tg & 127;

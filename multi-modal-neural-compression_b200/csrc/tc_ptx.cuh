@@ -58,6 +58,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void st_shared_u32(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
@@ -92,6 +99,12 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return r;
 }
+
+// Same rounding (nearest, ties away from zero, on the sign-magnitude bit pattern) in two integer instructions.
+// cvt.rna.tf32.f32 has no SASS instruction on sm_100a: ptxas expands it into ~6 instructions with Inf / NaN guards.
+// Here Inf stays Inf (mantissa 0), a NaN stays a NaN or becomes Inf only if its payload is all ones - irrelevant for
+// the finite activations this is used on.
+__device__ __forceinline__ uint32_t to_tf32_fast(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
 
 // shared-memory matrix descriptor: K-major, no swizzle.  Core matrix = 8 rows x 16 B stored as 128 contiguous
 // bytes; LBO = byte distance between core matrices adjacent in K, SBO = between 8-row groups (both >> 4).
