@@ -40,7 +40,7 @@ struct Bwd2Ctx {
     uint32_t sb;             // channel stride in bytes
     uint32_t stage0;         // shared address of stage 0 ([u | x2] per stage, R8 * 4096 bytes each)
     uint32_t gamma0;         // shared address of the gamma tile; gamma^T follows P * P * 4 bytes later
-    uint32_t full_bar0, mma_bar0;  // shared addresses of the mbarrier arrays
+    uint32_t full_bar0, mma_bar0, free_bar0;  // shared addresses of the mbarrier arrays
     uint32_t tmem_base;
     const void *tm_x, *tm_g;
     float *dx;
@@ -145,7 +145,8 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     const uint32_t lane_a = a_base + (((uint32_t)(((threadIdx.x >> 5) & 3) * 32)) << 16) + (uint32_t)c_begin;
     const uint32_t lane_d = lane_a + (uint32_t)P;
     const uint32_t lane_f = lane_a + (uint32_t)((NGROUPS * 3 - group) * P);  // columns after every A / D / D3 region
-    const uint32_t mbar = t.mma_bar0 + 8u * (uint32_t)group;
+    const uint32_t mbar = t.mma_bar0 + 8u * (uint32_t)group;    // MMA1 done / MMA2 done (alternating phases)
+    const uint32_t fbar = t.free_bar0 + 8u * (uint32_t)group;  // MMA3 done: the stage may be refilled, D3 is current
     // local channels TAIL0 + i with i < one_i are real, i == one_i is the constant-1 channel C, the rest is padding
     const int one_i = t.C - c_begin - TAIL0;
     // swizzled offset of (row c, pixel pix): rows of one 8-row group differ only in the XOR of address bits 4..6 with
@@ -248,19 +249,19 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         fence_async_smem();
         fence_before();
         named_bar_sync(bar_id, TPG);
-        // ---- MMA2: D = u * gamma (B = gamma^T tile);  MMA3: D3 += u^T x2 (K = 128 pixels of this stage)
+        // ---- MMA2: D = u * gamma (B = gamma^T tile), committed on its own so that epilogue 2 overlaps MMA3;
+        //      MMA3: D3 += u^T x2 (K = 128 pixels of this stage), committed to the "stage free" barrier
         if (leader) {
             fence_after();
             mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0 + (uint32_t)(P * P * 4), 128), GAMMA_HI, IDESC);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
             mma_ss_chain<0>(tmem_base + (uint32_t)(NGROUPS * 2 * P + group * P), desc_lo(us, 16), desc_lo(xs, 16), PIX_HI,
                             (uint32_t)t.R8 * 64u, IDESC, first ? 0u : 1u);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(fbar) : "memory");
         }
         mbar_wait_addr(mbar, parity);
         parity ^= 1;
         fence_after();
-        // the stage is free (MMA3 was its last reader): refill it with the tile NSTAGES ahead
-        if (leader && k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
         // ---- epilogue 2: dx = g n^p + 2 x t
         {
             const uint32_t tile = blockIdx.x + (uint32_t)k * gridDim.x;
@@ -283,11 +284,19 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                 }
             }
         }
-        fence_before();
-        named_bar_sync(bar_id, TPG);  // A and D of this group are free again
-        fence_after();
+        // No barrier here: the next tile's first barrier (after its A fill) already orders every thread's TMEM reads
+        // of this tile before the next MMA1 overwrites D, and A was last read by MMA2, which has completed.
+        // The stage is free once MMA3 (its last reader) has retired: refill it with the tile NSTAGES ahead.
+        if (leader) {
+            mbar_wait_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1));
+            if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
+        }
         first = false;
     }
+    // the leader has seen the last MMA3 retire; after this barrier D3 is final for the whole group
+    fence_before();
+    named_bar_sync(bar_id, TPG);
+    fence_after();
 #undef MMNC_REAL
 #undef MMNC_FRESH_OI
 #undef MMNC_SOFF
@@ -306,6 +315,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full_bar[NSTAGES];
     __shared__ uint64_t mma_bar[NGROUPS];
+    __shared__ uint64_t free_bar[NGROUPS];
     __shared__ uint32_t tmem_base_s;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int R8 = (C + 1 + 7) >> 3;
@@ -320,6 +330,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGES; ++s) mbar_init(&full_bar[s], 1);
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&mma_bar[q], 1);
+        for (int q = 0; q < NGROUPS; ++q) mbar_init(&free_bar[q], 1);
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_g);
     }
@@ -363,6 +374,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     ctx.gamma0 = smem_u32(Bs);
     ctx.full_bar0 = smem_u32(&full_bar[0]);
     ctx.mma_bar0 = smem_u32(&mma_bar[0]);
+    ctx.free_bar0 = smem_u32(&free_bar[0]);
     ctx.tmem_base = tmem_base_s;
     ctx.tm_x = &tm_x; ctx.tm_g = &tm_g;
     ctx.dx = dx;
