@@ -168,41 +168,58 @@ def time_kernel(torch, fn, reps=10):
 
 
 def roofline_of_gdn(torch, mm, harness, peak_gbs, peak_src, precision):
-    """Dominant kernel: the GDN contraction on the largest layer (first GDN of each input head).  The kernel is
-    launched alone (re-parametrised beta / gamma precomputed) on alternating 839 MB inputs (>> 126 MB L2)."""
+    """Dominant kernel of the step = the fused GDN backward on the largest layer (first GDN of each input head; the
+    backward launches are > 50 % of the step's GPU time, profiles/).  Both kernels are launched alone through the
+    C ABI (effective beta / gamma precomputed) on alternating 839 MB inputs (>> 126 MB L2) and timed with CUDA
+    events on the launching stream.  `traffic` is the ncu DRAM byte count of the same launch (profiles/)."""
+    L = mm._lib.lib()
+    prec = mm.ops.GDN_PRECISION[precision]
     big = sorted(harness.sites, key=lambda s: -s[1].numel())[:2]
     eff = []
     with torch.no_grad():
         for mod, x, g in big:
             eff.append((mod.beta_reparam(mod.beta).clone(), mod.gamma_reparam(mod.gamma).clone(), x.detach(), g,
                         mod.inverse))
+    x0 = eff[0][2]
+    B, C = x0.shape[:2]
+    HW = x0.numel() // (B * C)
+    n = x0.numel()
+    st = torch.cuda.current_stream().cuda_stream
+    y = torch.empty_like(x0)
+    dbeta, dgamma = torch.empty_like(eff[0][0]), torch.empty_like(eff[0][1])
+    nbytes = int(L.mmnc_gdn_backward_workspace_bytes(B, C, HW, prec))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x0.device)
     idx = [0]
 
     def fwd():
         b, gm, x, _, inv = eff[idx[0] % len(eff)]
         idx[0] += 1
-        return mm.ops.gdn(x, b, gm, inv, precision)
+        mm._lib.check(L.mmnc_gdn_forward(x.data_ptr(), B, C, HW, b.data_ptr(), gm.data_ptr(), int(inv), prec,
+                                         y.data_ptr(), st))
 
-    with torch.no_grad():
-        t_f = time_kernel(torch, fwd, reps=10)
-    x = eff[0][2]
-    n = x.numel()
-    out = {"roofline": {
-        "bound": "hbm", "kernel": "gdn forward, GDN(%d) on %dx%d, batch %d" % (x.shape[1], x.shape[2], x.shape[3], x.shape[0]),
-        "achieved": 8.0 * n / t_f / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": 8.0 * n / t_f / 1e9 / peak_gbs,
-        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": 8 * n, "launch_ms": t_f * 1e3}}
-
-    def fwd_bwd():
+    def bwd():
         b, gm, x, g, inv = eff[idx[0] % len(eff)]
         idx[0] += 1
-        xr, br, gr = x.requires_grad_(True), b.requires_grad_(True), gm.requires_grad_(True)
-        torch.autograd.grad(mm.ops.gdn(xr, br, gr, inv, precision), [xr, br, gr], g)
+        mm._lib.check(L.mmnc_gdn_backward(x.data_ptr(), g.data_ptr(), B, C, HW, b.data_ptr(), gm.data_ptr(), int(inv),
+                                          prec, y.data_ptr(), dbeta.data_ptr(), dgamma.data_ptr(), ws.data_ptr(),
+                                          nbytes, st))
 
-    t_b = max(time_kernel(torch, fwd_bwd, reps=5) - t_f, 1e-9)
-    out["roofline_backward"] = {"bound": "hbm", "kernel": "gdn backward, same layer (forward time subtracted)",
-                                "achieved": 12.0 * n / t_b / 1e9, "peak": peak_gbs, "unit": "GB/s",
-                                "frac": 12.0 * n / t_b / 1e9 / peak_gbs, "algorithmic_bytes_per_launch": 12 * n,
-                                "launch_ms": t_b * 1e3}
+    t_f = time_kernel(torch, fwd, reps=10)
+    t_b = time_kernel(torch, bwd, reps=10)
+    variant = int(L.mmnc_gdn_backward_variant(x0.data_ptr(), eff[0][3].data_ptr(), B, C, HW, prec))
+    shape = "GDN(%d) on %dx%d, batch %d" % (C, x0.shape[2], x0.shape[3], B)
+    # DRAM bytes of exactly this launch from `ncu --set full` (profiles/r01_ncu_summary.md); other shapes: unknown
+    ncu_traffic = {(64, 50, 65536): (2.480e9, 1.632e9)}.get((B, C, HW), (None, None))
+    out = {"roofline": {
+        "bound": "hbm", "kernel": "gdn backward (fused tcgen05, %s), %s; includes its ~10 us partial-reduce launch"
+                                  % ({3: "TMA-fed pipelined", 2: "first generation"}.get(variant, "variant %d" % variant), shape),
+        "achieved": 12.0 * n / t_b / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": 12.0 * n / t_b / 1e9 / peak_gbs,
+        "traffic": ncu_traffic[0], "peak_source": peak_src, "algorithmic_bytes_per_launch": 12 * n,
+        "launch_ms": t_b * 1e3}}
+    out["roofline_forward"] = {
+        "bound": "hbm", "kernel": "gdn forward (tcgen05), " + shape,
+        "achieved": 8.0 * n / t_f / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": 8.0 * n / t_f / 1e9 / peak_gbs,
+        "traffic": ncu_traffic[1], "algorithmic_bytes_per_launch": 8 * n, "launch_ms": t_f * 1e3}
     return out
 
 

@@ -22,6 +22,15 @@ struct GdnParams {
         if (raw) { v = max_nan(v, gamma_bound); v = v * v - pedestal; }
         return v;
     }
+    // the same two maps applied to a value that has already been loaded (staging loops issue all their loads first)
+    __device__ __forceinline__ float b_of(float v) const {
+        if (raw) { v = max_nan(v, beta_bound); v = v * v - pedestal; }
+        return v;
+    }
+    __device__ __forceinline__ float g_of(float v) const {
+        if (raw) { v = max_nan(v, gamma_bound); v = v * v - pedestal; }
+        return v;
+    }
     // chain rule back to the raw parameter, with LowerBound's custom gradient
     __device__ __forceinline__ float db(int i, float d_eff) const {
         if (!raw) return d_eff;

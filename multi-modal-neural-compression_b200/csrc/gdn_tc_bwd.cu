@@ -249,19 +249,39 @@ gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g,
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
     // gamma tile: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]); column k = C holds beta; zero elsewhere in the padding
+    // Loads first (eight elements = sixteen loads per thread in flight), then the arithmetic: one dependent L2 round
+    // trip per element made this loop ~30 us per CTA at C = 100.
     constexpr int kcores = P >> 2;
-    for (int idx = threadIdx.x; idx < P * P; idx += THREADS) {
-        const int n = idx / P, k = idx - n * P;
-        float v = 0.f;
-        if (n < C && k < C) v = prm.g((int64_t)n * C + k);
-        else if (n < C && k == C) v = prm.b(n);
-        else if (n >= C && k == C) v = 1.f;  // padded outputs get norm = 1 (finite)
-        const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
-        reinterpret_cast<uint32_t *>(Bs)[off] = to_tf32(v);
-        // transposed copy for MMA2 (a K-major operand again; tf32 MN-major reads of the same tile returned zeros
-        // on sm_100a, so the transpose is materialised once per CTA instead)
-        const float vt = (n < C && k < C) ? prm.g((int64_t)k * C + n) : 0.f;
-        reinterpret_cast<uint32_t *>(Bs2)[off] = to_tf32(vt);
+    constexpr int SU = 8;
+    for (int base = threadIdx.x; base < P * P; base += THREADS * SU) {
+        float raw[SU], rawt[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int idx = base + u * THREADS;
+            const int n = idx / P, k = idx - n * P;
+            float v = 0.f, vt = 0.f;
+            if (idx < P * P) {
+                if (n < C && k < C) { v = prm.gamma[(int64_t)n * C + k]; vt = prm.gamma[(int64_t)k * C + n]; }
+                else if (n < C && k == C) v = prm.beta[n];
+            }
+            raw[u] = v; rawt[u] = vt;
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int idx = base + u * THREADS;
+            if (idx >= P * P) break;
+            const int n = idx / P, k = idx - n * P;
+            float v = 0.f;
+            if (n < C && k < C) v = prm.g_of(raw[u]);
+            else if (n < C && k == C) v = prm.b_of(raw[u]);
+            else if (n >= C && k == C) v = 1.f;  // padded outputs get norm = 1 (finite)
+            const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
+            reinterpret_cast<uint32_t *>(Bs)[off] = to_tf32(v);
+            // transposed copy for MMA2 (a K-major operand again; tf32 MN-major reads of the same tile returned zeros
+            // on sm_100a, so the transpose is materialised once per CTA instead)
+            const float vt = (n < C && k < C) ? prm.g_of(rawt[u]) : 0.f;
+            reinterpret_cast<uint32_t *>(Bs2)[off] = to_tf32(vt);
+        }
     }
     // rows of the two pixel-major operands that no thread writes (r in [P', 8 R8)) must stay finite: zero them
     for (uint32_t i = threadIdx.x; i < 2 * buf_bytes / 4; i += THREADS) reinterpret_cast<uint32_t *>(smem)[i] = 0u;
@@ -345,7 +365,7 @@ bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW) {
     int P;
     uint32_t cols;
     size_t smem;
-    return tcb_geometry(C, &P, &cols, &smem) && B * HW >= 4096 && HW < (1 << 24);
+    return tcb_geometry(C, &P, &cols, &smem) && B * HW >= 128 && HW < (1 << 24);
 }
 
 static int tcb_grid(int64_t NP, uint32_t tmem_cols, size_t smem) {

@@ -335,17 +335,39 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         tma_prefetch_desc(&tm_g);
     }
     // gamma tiles, as in gdn_tc_bwd.cu: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]); column k = C holds beta
+    // Loads first (eight elements = sixteen loads per thread in flight), then the arithmetic: one dependent L2 round
+    // trip per element made this loop ~30 us per CTA at C = 100.
     constexpr int kcores = P >> 2;
-    for (int idx = threadIdx.x; idx < P * P; idx += THREADS) {
-        const int n = idx / P, k = idx - n * P;
-        float v = 0.f;
-        if (n < C && k < C) v = prm.g((int64_t)n * C + k);
-        else if (n < C && k == C) v = prm.b(n);
-        else if (n >= C && k == C) v = 1.f;  // padded outputs get norm = 1 (finite)
-        const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
-        reinterpret_cast<uint32_t *>(Bs)[off] = to_tf32(v);
-        const float vt = (n < C && k < C) ? prm.g((int64_t)k * C + n) : 0.f;
-        reinterpret_cast<uint32_t *>(Bs2)[off] = to_tf32(vt);
+    constexpr int SU = 8;
+    for (int base = threadIdx.x; base < P * P; base += THREADS * SU) {
+        float raw[SU], rawt[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int idx = base + u * THREADS;
+            const int n = idx / P, k = idx - n * P;
+            float v = 0.f, vt = 0.f;
+            if (idx < P * P) {
+                if (n < C && k < C) { v = prm.gamma[(int64_t)n * C + k]; vt = prm.gamma[(int64_t)k * C + n]; }
+                else if (n < C && k == C) v = prm.beta[n];
+            }
+            raw[u] = v; rawt[u] = vt;
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int idx = base + u * THREADS;
+            if (idx >= P * P) break;
+            const int n = idx / P, k = idx - n * P;
+            float v = 0.f;
+            if (n < C && k < C) v = prm.g_of(raw[u]);
+            else if (n < C && k == C) v = prm.b_of(raw[u]);
+            else if (n >= C && k == C) v = 1.f;  // padded outputs get norm = 1 (finite)
+            const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
+            reinterpret_cast<uint32_t *>(Bs)[off] = to_tf32(v);
+            // transposed copy for MMA2 (a K-major operand again; tf32 MN-major reads of the same tile returned zeros
+            // on sm_100a, so the transpose is materialised once per CTA instead)
+            const float vt = (n < C && k < C) ? prm.g_of(rawt[u]) : 0.f;
+            reinterpret_cast<uint32_t *>(Bs2)[off] = to_tf32(vt);
+        }
     }
     // landing stages: rows the TMA box never writes (r >= C) are 0, except row C of every x2 buffer = the constant 1
     {
