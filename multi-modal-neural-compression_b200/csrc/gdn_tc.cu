@@ -201,6 +201,11 @@ gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// gdn_tc_fwd2.cu: the TMA-in / TMA-out generation of this kernel (single-pass TF32, HW % 128 == 0 only)
+bool gdn_tc_forward2_supported(const float *x, const float *y, int64_t B, int64_t C, int64_t HW);
+int gdn_tc_forward2(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, float *y,
+                    cudaStream_t s);
+
 static bool tc_geometry(int64_t C, bool k3x, tc::Geometry *g) {
     if (C < 8 || C > 128) return false;  // the pixel's channels live in registers: C <= 128
     g->C = (int)C;
@@ -228,6 +233,7 @@ int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnPa
                    float *y, cudaStream_t s) {
     tc::Geometry g;
     const bool k3x = (precision == MMNC_GDN_3XTF32);
+    if (!k3x && gdn_tc_forward2_supported(x, y, B, C, HW)) return gdn_tc_forward2(x, B, C, HW, prm, inverse, y, s);
     if (!tc_geometry(C, k3x, &g)) {
         set_error("gdn_tc_forward: C = %lld not supported by the tensor-core path", (long long)C);
         return MMNC_ERR_UNSUPPORTED;

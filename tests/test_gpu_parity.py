@@ -359,6 +359,29 @@ def test_gdn_backward_tensor_core(shape, inverse):
 
 
 
+
+# (KP8 -> groups, stages) instances of gdn_tc_fwd2.cu: C=16/20 -> 4 groups, 33/40 -> 3, 50/64 -> 2, 100/104 -> 1 x 3 stages,
+# 128 -> 1 x 2 stages; C % 8 == 0 takes beta from shared memory, otherwise through the constant MMA column
+@pytest.mark.parametrize("shape", [(10, 50, 64, 64), (5, 100, 128, 64), (10, 64, 64, 64), (12, 20, 64, 64),
+                                   (10, 40, 32, 128), (10, 33, 64, 64), (10, 104, 64, 64), (10, 128, 64, 64),
+                                   (20, 16, 16, 128)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_forward_tensor_core_tma(shape, inverse):
+    """TMA-in / TMA-out tcgen05 forward (gdn_tc_fwd2.cu) against the oracle; single-pass TF32 tolerance 1e-3."""
+    torch.manual_seed(19)
+    ours, ref = _pair_gdn(shape[1], inverse, precision="tf32")
+    x = torch.randn(*shape)
+    xd = x.to(DEV)
+    before = mm.launch_count()
+    y = ours(xd)
+    torch.cuda.synchronize()
+    assert mm.launch_count() == before + 1
+    want = ref(x)
+    assert torch.allclose(y.detach().cpu(), want, rtol=1e-3, atol=1e-4), (y.detach().cpu() - want).abs().max()
+    assert torch.equal(ours(xd[1:3].contiguous()), y[1:3]), "batch independence"
+    assert torch.equal(xd.cpu(), x), "the input must not be modified (y is written in place in shared memory only)"
+
+
 def _gdn_bwd_variant(x, g, precision="tf32"):
     B, C = x.shape[:2]
     HW = x.numel() // (B * C)
@@ -415,6 +438,9 @@ def test_gdn_backward_pipelined_long_sequences(shape):
         outs.append(torch.autograd.grad(mm.ops.gdn(xr, br, gr, False, prec), [xr, br, gr], g))
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b), "pipelined backward is not deterministic"
+    with torch.no_grad():  # the forward of the same layers (dozens of tiles per compute group) against fp32
+        y_tc, y_32 = mm.ops.gdn(x, beta, gamma, False, "tf32"), mm.ops.gdn(x, beta, gamma, False, "fp32")
+    assert torch.allclose(y_tc, y_32, rtol=1e-3, atol=1e-4)
     for a, b in zip(outs[0], outs[2]):
         assert ((a - b).abs().max() / b.abs().max()).item() <= 2e-3
 
