@@ -25,7 +25,6 @@
 namespace mmnc {
 
 namespace tcb2 {
-constexpr int TPG = 256;   // threads per compute group: thread t and t + 128 share a pixel and split the channels
 constexpr int TILE = 128;  // pixels per tile = TMEM lanes
 }  // namespace tcb2
 
@@ -118,13 +117,19 @@ __device__ __forceinline__ void tmem_stw(uint32_t taddr, const uint32_t (&r)[W])
 // the instruction footprint inside the instruction cache (ncu: 21 % of the stalls were instruction fetches with two
 // copies).  Channel offsets are folded into the per-thread TMEM / shared / global bases; only the last 16 channels of
 // a thread can be padding, and a 16-bit mask says which.
-template <int KH8, int NGROUPS, int NSTAGES, bool kInverse>
+template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse>
 __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int group, int tg) {
     using namespace tc;
     using namespace tcb2;
-    constexpr int KH = KH8 * 8;   // channels handled by this thread
-    constexpr int P = KH * 2;     // padded channel count
-    constexpr int TAIL0 = (KH > 16) ? KH - 16 : 0;  // first local channel that may be padding (C > P - 16)
+    constexpr int P = KH8 * 16;   // padded channel count
+    // TPP threads share a pixel (a TMEM lane) and own contiguous channel ranges of KH channels: P / 2 each for two
+    // threads; for four, P / 4 rounded up to 8 (the last thread's range then runs past P: those blocks are skipped).
+    // Measured on B200: four threads per pixel (with f parked in TMEM to fit 128 registers) is SLOWER on the wide,
+    // single-group layers (GDN(100)@128^2: 0.444 vs 0.390 ms), so every instance below uses two.
+    constexpr int KH = (TPP == 2) ? P / 2 : (P / 4 + 7) / 8 * 8;
+    constexpr int TPG = 128 * TPP;
+    // first local channel that may be padding: with two threads only the last 16 channels of a thread (C > P - 16)
+    constexpr int TAIL0 = (TPP == 2 && KH > 16) ? KH - 16 : 0;
     constexpr float coef = kInverse ? 0.5f : -0.5f;
     // two groups = 128 registers per thread: g is then re-read from its landing buffer in epilogue 1 and f = g n^p
     // is parked in spare TMEM columns until epilogue 2, so that only x stays in registers across the MMA waits
@@ -185,6 +190,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         //      whose shared-memory row was written once at start-up and is never touched by the TMA box (C rows)
 #pragma unroll
         for (int j0 = 0; j0 < KH; j0 += W) {
+            if (TPP > 2 && c_begin + j0 >= P) break;  // (warp-uniform) columns past the A region belong to D
             uint32_t v[W];
 #pragma unroll
             for (int j = 0; j < W; ++j) {
@@ -215,6 +221,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         MMNC_FRESH_OI();
 #pragma unroll
         for (int j0 = 0; j0 < KH; j0 += W1) {
+            if (TPP > 2 && c_begin + j0 >= P) break;
             uint32_t r[W1], uu[W1], ff[W1];
             float g8[W1];
             tmem_ldw<W1>(lane_d + j0, r);
@@ -272,6 +279,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
             float *dxb = t.dx + ((int64_t)(b * (uint32_t)t.C + (uint32_t)c_begin) * (int64_t)(sb >> 2) + hw0 + pix);
 #pragma unroll
             for (int j0 = 0; j0 < KH; j0 += W) {
+                if (TPP > 2 && c_begin + j0 >= P) break;
                 uint32_t r[W], ff[W];
                 tmem_ldw<W>(lane_d + j0, r);
                 if constexpr (PARK) tmem_ldw<W>(lane_f + j0, ff);
@@ -303,14 +311,15 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     return first;
 }
 
-template <int KH8, int NGROUPS, int NSTAGES, bool kInverse>
-__global__ void __launch_bounds__(NGROUPS *tcb2::TPG, 1)
+template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse>
+__global__ void __launch_bounds__(NGROUPS * TPP * 128, 1)
 gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                         int ntiles, int tiles_per_img, int HW, const GdnParams prm, float *__restrict__ dx,
                         float *__restrict__ part, int C, uint32_t tmem_cols) {
     using namespace tc;
     using namespace tcb2;
     constexpr int P = KH8 * 16;
+    constexpr int TPG = 128 * TPP;
     constexpr int THREADS = NGROUPS * TPG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full_bar[NSTAGES];
@@ -409,7 +418,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const int pre = n_k < NSTAGES ? n_k : NSTAGES;
         for (int k = 0; k < pre; ++k) bwd2_issue_tile<NSTAGES>(ctx, k);
     }
-    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, kInverse>(ctx, group, tg);
+    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, TPP, kInverse>(ctx, group, tg);
     // ---- this group's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
     float *dst = part + ((int64_t)blockIdx.x * NGROUPS + group) * C * (C + 1);
     const int pix = tg & 127;
@@ -588,7 +597,7 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, int, const GdnParams, float *, float *,
                             int, uint32_t);
     Kernel kernel = nullptr;
-#define MMNC_PICK(N, G, S) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, true> : (Kernel)gdn_tc_backward2_kernel<N, G, S, false>)
+#define MMNC_PICK(N, G, S) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, true> : (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, false>)
     const int key = (geo.P / 16) * 100 + geo.groups * 10 + geo.stages;
     switch (key) {
         case 223: kernel = MMNC_PICK(2, 2, 3); break;
@@ -607,7 +616,7 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     }
     MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
     float *part = static_cast<float *>(workspace);
-    kernel<<<(unsigned)grid, geo.groups * tcb2::TPG, geo.smem, s>>>(tm_x, tm_g, (int)ntiles, (int)(HW / tcb2::TILE), (int)HW,
+    kernel<<<(unsigned)grid, geo.groups * 2 * 128, geo.smem, s>>>(tm_x, tm_g, (int)ntiles, (int)(HW / tcb2::TILE), (int)HW,
                                                                    prm, dx, part, (int)C, geo.tmem_cols);
     if (int rc = after_launch("gdn_tc_backward2_kernel")) return rc;
     return gdn_reduce_partials(part, ksplit, (int)C, prm, dgamma, dbeta, s);
