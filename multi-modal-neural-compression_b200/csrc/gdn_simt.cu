@@ -155,31 +155,48 @@ gdn_dgamma_kernel(const float *__restrict__ U, const float *__restrict__ x, int6
 }
 
 // one warp per output element: lanes stride over the partials, then a shuffle tree — a fixed summation order
+// Fixed-order sum of the per-CTA partials.  Block = 32 consecutive elements x 8 slices of the partial index: a warp
+// reads 128 contiguous bytes of one partial (the old one-warp-per-element mapping fetched 32 sectors per load), four
+// independent accumulators per thread keep the loads in flight, and the 8 slices are combined through shared memory.
+// (Few elements, e.g. C = 3: EX = 8 elements x 32 slices per block instead, so that the partial index is still spread.)
+template <int EX>
 __global__ void __launch_bounds__(256)
 gdn_reduce_kernel(const float *__restrict__ part, int ksplit, int C, const GdnParams prm,
                   float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    constexpr int SL = 256 / EX;  // slices of the partial index
+    __shared__ float red[SL][EX + 1];
     const int CJ = C + 1;
     const int64_t n = (int64_t)C * CJ;
-    const int lane = threadIdx.x & 31;
-    for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n;
-         e += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-        float s = 0.f;
-        for (int k = lane; k < ksplit; k += 32) s += part[(int64_t)k * n + e];
-        s = warp_sum(s);
-        if (lane == 0) {
-            const int i = (int)(e / CJ), j = (int)(e - (int64_t)i * CJ);
-            if (j < C) dgamma[(int64_t)i * C + j] = prm.dg((int64_t)i * C + j, s); else dbeta[i] = prm.db(i, s);
+    const int ex = threadIdx.x % EX, ky = threadIdx.x / EX;
+    const int64_t e = (int64_t)blockIdx.x * EX + ex;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (e < n) {
+        const float *p = part + e;
+        int k = ky;
+        for (; k + 3 * SL < ksplit; k += 4 * SL) {
+            a0 += p[(int64_t)k * n];
+            a1 += p[(int64_t)(k + SL) * n];
+            a2 += p[(int64_t)(k + 2 * SL) * n];
+            a3 += p[(int64_t)(k + 3 * SL) * n];
         }
+        for (; k < ksplit; k += SL) a0 += p[(int64_t)k * n];
+    }
+    red[ky][ex] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ky == 0 && e < n) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < SL; ++q) s += red[q][ex];
+        const int i = (int)(e / CJ), j = (int)(e - (int64_t)i * CJ);
+        if (j < C) dgamma[(int64_t)i * C + j] = prm.dg((int64_t)i * C + j, s); else dbeta[i] = prm.db(i, s);
     }
 }
 
 int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &prm, float *dgamma, float *dbeta,
                         cudaStream_t s) {
     const int64_t n = (int64_t)C * (C + 1);
-    int64_t blocks = (n + 7) / 8;  // 8 warps per block, one element per warp
-    const int64_t cap = (int64_t)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    gdn_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
+    if (n >= 2048) gdn_reduce_kernel<32><<<(unsigned)((n + 31) / 32), 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
+    else gdn_reduce_kernel<8><<<(unsigned)((n + 7) / 8), 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
     return after_launch("gdn_reduce_kernel");
 }
 

@@ -118,7 +118,7 @@ __device__ __forceinline__ void tmem_stw(uint32_t taddr, const uint32_t (&r)[W])
 // copies).  Channel offsets are folded into the per-thread TMEM / shared / global bases; only the last 16 channels of
 // a thread can be padding, and a 16-bit mask says which.
 template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse>
-__device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int group, int tg) {
+__device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int group, int tg, uint32_t tmem_base_in) {
     using namespace tc;
     using namespace tcb2;
     constexpr int P = KH8 * 16;   // padded channel count
@@ -145,7 +145,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     const int c_begin = (tg >> 7) * KH;
     const bool leader = (tg == 0);
     const uint32_t bar_id = 1u + (uint32_t)group;
-    const uint32_t tmem_base = t.tmem_base;
+    const uint32_t tmem_base = tmem_base_in;
     const uint32_t a_base = tmem_base + (uint32_t)(group * 2 * P);
     const uint32_t lane_a = a_base + (((uint32_t)(((threadIdx.x >> 5) & 3) * 32)) << 16) + (uint32_t)c_begin;
     const uint32_t lane_d = lane_a + (uint32_t)P;
@@ -335,6 +335,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     const int warp = threadIdx.x >> 5;
     const int group = threadIdx.x / TPG, tg = threadIdx.x % TPG;
 
+    __shared__ Bwd2Ctx ctx_s;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGES; ++s) mbar_init(&full_bar[s], 1);
@@ -342,6 +343,29 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&free_bar[q], 1);
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_g);
+        Bwd2Ctx c;
+        c.C = C; c.R8 = R8;
+        c.tiles_per_img = tiles_per_img;
+        c.n_k = (blockIdx.x < (uint32_t)ntiles) ? (int)(((uint32_t)ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+        c.sb = (uint32_t)HW * 4u;
+        c.stage0 = smem_u32(smem);
+        c.gamma0 = smem_u32(Bs);
+        c.full_bar0 = smem_u32(&full_bar[0]);
+        c.mma_bar0 = smem_u32(&mma_bar[0]);
+        c.free_bar0 = smem_u32(&free_bar[0]);
+        c.tmem_base = 0;  // read from tmem_base_s once the allocation is visible
+        c.tm_x = &tm_x; c.tm_g = &tm_g;
+        c.dx = dx;
+        ctx_s = c;
+    }
+    __syncthreads();
+    const volatile Bwd2Ctx &ctx = ctx_s;
+    // the first NSTAGES tiles are on their way while gamma is being staged (small layers are all prologue); the TMA
+    // box writes rows < C only, the loop below initialises rows >= C only
+    if (threadIdx.x == 0) {
+        const int n_k = ctx.n_k;
+        const int pre = n_k < NSTAGES ? n_k : NSTAGES;
+        for (int k = 0; k < pre; ++k) bwd2_issue_tile<NSTAGES>(ctx, k);
     }
     // gamma tiles, as in gdn_tc_bwd.cu: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]); column k = C holds beta
     // Loads first (eight elements = sixteen loads per thread in flight), then the arithmetic: one dependent L2 round
@@ -378,47 +402,25 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
             reinterpret_cast<uint32_t *>(Bs2)[off] = to_tf32(vt);
         }
     }
-    // landing stages: rows the TMA box never writes (r >= C) are 0, except row C of every x2 buffer = the constant 1
+    // landing stages: rows the TMA box never writes (C <= r < 8 R8) are 0, except row C of every x2 buffer = the constant 1
     {
-        const uint32_t words_per_buf = buf_bytes >> 2, words = (uint32_t)NSTAGES * 2u * words_per_buf;
-        const uint32_t atom_words = (uint32_t)R8 * 256u;
+        const int pad_rows = 8 * R8 - C;                                   // 1 .. 8
+        const uint32_t per_buf = 4u * (uint32_t)pad_rows * 32u;            // 4 K atoms x pad rows x 32 words
+        const uint32_t words = (uint32_t)NSTAGES * 2u * per_buf;
         for (uint32_t i = threadIdx.x; i < words; i += THREADS) {
-            const uint32_t buf = i / words_per_buf, o = i - buf * words_per_buf;
-            const uint32_t oa = o % atom_words;
-            const int r = (int)((oa >> 8) << 3) + (int)((oa >> 5) & 7);  // 1024 B per 8-row group, 128 B per row
-            reinterpret_cast<uint32_t *>(smem)[i] = ((buf & 1u) && r == C) ? 0x3f800000u : 0u;
+            const uint32_t buf = i / per_buf, o = i - buf * per_buf;
+            const uint32_t atom = o / ((uint32_t)pad_rows * 32u), o2 = o - atom * (uint32_t)pad_rows * 32u;
+            const int r = C + (int)(o2 >> 5);
+            const uint32_t w = o2 & 31u;
+            const uint32_t byte = buf * buf_bytes + ((atom * (uint32_t)R8 + (uint32_t)(r >> 3)) << 10) + ((uint32_t)(r & 7) << 7) + (w << 2);
+            *reinterpret_cast<uint32_t *>(smem + byte) = ((buf & 1u) && r == C) ? 0x3f800000u : 0u;
         }
     }
     fence_async_smem();
     fence_before();
     __syncthreads();
     fence_after();
-
-    __shared__ Bwd2Ctx ctx_s;
-    if (threadIdx.x == 0) {
-    Bwd2Ctx ctx;
-    ctx.C = C; ctx.R8 = R8;
-    ctx.tiles_per_img = tiles_per_img;
-    ctx.n_k = (blockIdx.x < (uint32_t)ntiles) ? (int)(((uint32_t)ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-    ctx.sb = (uint32_t)HW * 4u;
-    ctx.stage0 = smem_u32(smem);
-    ctx.gamma0 = smem_u32(Bs);
-    ctx.full_bar0 = smem_u32(&full_bar[0]);
-    ctx.mma_bar0 = smem_u32(&mma_bar[0]);
-    ctx.free_bar0 = smem_u32(&free_bar[0]);
-    ctx.tmem_base = tmem_base_s;
-    ctx.tm_x = &tm_x; ctx.tm_g = &tm_g;
-    ctx.dx = dx;
-    ctx_s = ctx;
-    }
-    __syncthreads();
-    const volatile Bwd2Ctx &ctx = ctx_s;
-    if (threadIdx.x == 0) {
-        const int n_k = ctx.n_k;
-        const int pre = n_k < NSTAGES ? n_k : NSTAGES;
-        for (int k = 0; k < pre; ++k) bwd2_issue_tile<NSTAGES>(ctx, k);
-    }
-    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, TPP, kInverse>(ctx, group, tg);
+    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, TPP, kInverse>(ctx, group, tg, tmem_base_s);
     // ---- this group's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
     float *dst = part + ((int64_t)blockIdx.x * NGROUPS + group) * C * (C + 1);
     const int pix = tg & 127;
@@ -530,7 +532,6 @@ bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64
         B * C >= (1ll << 31))
         return false;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(g) & 15)) return false;
-    if (B * HW / tcb2::TILE < 2 * (int64_t)sm_count() && bwd2_mode() != 2) return false;  // too few tiles to pipeline
     return encode_tiled() != nullptr;
 }
 

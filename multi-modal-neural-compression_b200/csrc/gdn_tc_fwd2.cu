@@ -101,7 +101,40 @@ gdn_tc_forward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&mma_bar[q], 1);
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_y);
+        Fwd2Ctx c;
+        c.C = C;
+        c.n_k = (blockIdx.x < (uint32_t)ntiles) ? (int)(((uint32_t)ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+        c.tiles_per_img = tiles_per_img;
+        c.stage0 = smem_u32(smem);
+        c.gamma0 = smem_u32(Bs);
+        c.beta0 = smem_u32(beta_s);
+        c.full_bar0 = smem_u32(&full_bar[0]);
+        c.mma_bar0 = smem_u32(&mma_bar[0]);
+        c.tmem_base = 0;
+        c.tm_x = &tm_x;
+        c.tm_y = &tm_y;
+        ctx_s = c;
     }
+    __syncthreads();
+    const volatile Fwd2Ctx &t = ctx_s;
+    // ---- this group's tile sequence: group-local tile kk <-> CTA tile kk * NGROUPS + group
+    const int n_g = (t.n_k - group + NGROUPS - 1) / NGROUPS;  // tiles of this group (may be <= 0)
+    const uint32_t ring0 = t.stage0 + (uint32_t)(group * NSTAGES) * stage_bytes;
+    const uint32_t fbar0 = t.full_bar0 + 8u * (uint32_t)(group * NSTAGES);
+    const uint32_t bytes = (uint32_t)C * 512u;
+    auto issue_load = [&](int kk) {
+        int b, hw0;
+        fwd2_coords(t, NGROUPS, group, kk, &b, &hw0);
+        const uint32_t bar = fbar0 + 8u * (uint32_t)(kk % NSTAGES);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(ring0 + (uint32_t)(kk % NSTAGES) * stage_bytes), "l"(reinterpret_cast<uint64_t>(t.tm_x)), "r"(hw0),
+              "r"(0), "r"(b), "r"(bar)
+            : "memory");
+    };
+    // the first tile of every group is on its way while gamma is being staged (small layers are all prologue)
+    if (leader && n_g > 0) issue_load(0);
     // B operand: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]) (zero padded; column k = Kp-1 holds beta when kBetaInMma);
     // loads first, eight per thread in flight, then the arithmetic
     {
@@ -137,48 +170,12 @@ gdn_tc_forward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     fence_before();
     __syncthreads();
     fence_after();
-    if (threadIdx.x == 0) {
-        Fwd2Ctx c;
-        c.C = C;
-        c.n_k = (blockIdx.x < (uint32_t)ntiles) ? (int)(((uint32_t)ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-        c.tiles_per_img = tiles_per_img;
-        c.stage0 = smem_u32(smem);
-        c.gamma0 = smem_u32(Bs);
-        c.beta0 = smem_u32(beta_s);
-        c.full_bar0 = smem_u32(&full_bar[0]);
-        c.mma_bar0 = smem_u32(&mma_bar[0]);
-        c.tmem_base = tmem_base_s;
-        c.tm_x = &tm_x;
-        c.tm_y = &tm_y;
-        ctx_s = c;
-    }
-    __syncthreads();
-    const volatile Fwd2Ctx &t = ctx_s;
-
-    // ---- this group's tile sequence: group-local tile kk <-> CTA tile kk * NGROUPS + group
-    const int n_g = (t.n_k - group + NGROUPS - 1) / NGROUPS;  // tiles of this group (may be <= 0)
     const uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t ring0 = t.stage0 + (uint32_t)(group * NSTAGES) * stage_bytes;
-    const uint32_t fbar0 = t.full_bar0 + 8u * (uint32_t)(group * NSTAGES);
     const uint32_t mbar = t.mma_bar0 + 8u * (uint32_t)group;
-    const uint32_t a_base = t.tmem_base + (uint32_t)group * (uint32_t)(Kp + Np);
+    const uint32_t a_base = tmem_base_s + (uint32_t)group * (uint32_t)(Kp + Np);
     const uint32_t d_base = a_base + (uint32_t)Kp;
     const uint32_t lane_sel = ((uint32_t)((warp & 3) * 32)) << 16;
     const uint32_t bar_id = 1u + (uint32_t)group;
-    const uint32_t bytes = (uint32_t)C * 512u;
-
-    auto issue_load = [&](int kk) {
-        int b, hw0;
-        fwd2_coords(t, NGROUPS, group, kk, &b, &hw0);
-        const uint32_t bar = fbar0 + 8u * (uint32_t)(kk % NSTAGES);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(ring0 + (uint32_t)(kk % NSTAGES) * stage_bytes), "l"(reinterpret_cast<uint64_t>(t.tm_x)), "r"(hw0),
-              "r"(0), "r"(b), "r"(bar)
-            : "memory");
-    };
-    if (leader && n_g > 0) issue_load(0);
 
     uint32_t parity = 0;
 #pragma unroll 1
@@ -367,7 +364,6 @@ bool gdn_tc_forward2_supported(const float *x, const float *y, int64_t B, int64_
     if (geo.stages < 3 && fwd2_mode() != 2) return false;  // two-stage rings (C > 112) measured slower than gdn_tc.cu
     if (HW % tcf2::TILE != 0 || HW >= (1 << 24) || B >= (1 << 24) || B * HW / tcf2::TILE >= (1ll << 31)) return false;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
-    if (B * HW / tcf2::TILE < 2 * (int64_t)sm_count() && fwd2_mode() != 2) return false;  // too few tiles to pipeline
     return fwd2_encode() != nullptr;
 }
 
