@@ -36,13 +36,36 @@ gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_
         for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {
             const int i0 = chunk * GDN_CH;
             __syncthreads();
-            for (int idx = threadIdx.x; idx < C * GDN_CH; idx += GDN_TP) {
-                if (MODE == 2) {  // W[i][kk] = gamma[i][i0 + kk]
-                    const int i = idx / GDN_CH, kk = idx - i * GDN_CH;
-                    W[idx] = (i0 + kk < C) ? prm.g((int64_t)i * C + i0 + kk) : 0.f;
-                } else {          // W[j][ii] = gamma[i0 + ii][j]
-                    const int ii = idx / C, j = idx - ii * C;
-                    W[j * GDN_CH + ii] = (i0 + ii < C) ? prm.g((int64_t)(i0 + ii) * C + j) : 0.f;
+            // loads first (eight per thread in flight), then the re-parametrisation and the shared-memory stores:
+            // one dependent L2 round trip per element made this staging loop the longest part of a small layer
+            for (int sbase = threadIdx.x; sbase < C * GDN_CH; sbase += GDN_TP * 8) {
+                float raw[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = sbase + u * GDN_TP;
+                    float v = 0.f;
+                    if (idx < C * GDN_CH) {
+                        if (MODE == 2) {  // W[i][kk] = gamma[i][i0 + kk]
+                            const int i = idx / GDN_CH, kk = idx - i * GDN_CH;
+                            if (i0 + kk < C) v = prm.gamma[(int64_t)i * C + i0 + kk];
+                        } else {          // W[j][ii] = gamma[i0 + ii][j]
+                            const int ii = idx / C, j = idx - ii * C;
+                            if (i0 + ii < C) v = prm.gamma[(int64_t)(i0 + ii) * C + j];
+                        }
+                    }
+                    raw[u] = v;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = sbase + u * GDN_TP;
+                    if (idx >= C * GDN_CH) break;
+                    if (MODE == 2) {
+                        const int i = idx / GDN_CH, kk = idx - i * GDN_CH;
+                        W[idx] = (i0 + kk < C) ? prm.g_of(raw[u]) : 0.f;
+                    } else {
+                        const int ii = idx / C, j = idx - ii * C;
+                        W[j * GDN_CH + ii] = (i0 + ii < C) ? prm.g_of(raw[u]) : 0.f;
+                    }
                 }
             }
             __syncthreads();
@@ -50,7 +73,7 @@ gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_
             float acc[GDN_CH];
 #pragma unroll
             for (int k = 0; k < GDN_CH; ++k) acc[k] = 0.f;
-#pragma unroll 4
+#pragma unroll 16
             for (int j = 0; j < C; ++j) {
                 float v = xin[(int64_t)j * HW];
                 if (MODE != 2) v = v * v;
@@ -64,22 +87,31 @@ gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_
                     acc[4 * q + 3] += v * w.w;
                 }
             }
+            float xi_v[GDN_CH], gi_v[GDN_CH], be_v[GDN_CH];
+#pragma unroll
+            for (int ii = 0; ii < GDN_CH; ++ii) {  // every load of the epilogue in flight before the first use
+                const int i = (i0 + ii < C) ? i0 + ii : C - 1;
+                const int64_t a = base + (int64_t)i * HW;
+                xi_v[ii] = x[a];
+                gi_v[ii] = (MODE == 1) ? g[a] : 0.f;
+                be_v[ii] = (MODE != 2) ? prm.beta[i] : 0.f;
+            }
 #pragma unroll
             for (int ii = 0; ii < GDN_CH; ++ii) {
                 const int i = i0 + ii;
                 if (i >= C) break;
                 const int64_t a = base + (int64_t)i * HW;
-                const float xi = x[a];
+                const float xi = xi_v[ii];
                 if (MODE == 2) {
                     out[a] += 2.f * xi * acc[ii];
                 } else {
-                    const float n = prm.b(i) + acc[ii];
+                    const float n = prm.b_of(be_v[ii]) + acc[ii];
                     const float rt = sqrtf(n);
                     const float pw = inverse ? rt : 1.f / rt;  // n^p
                     if (MODE == 0) {
                         out[a] = xi * pw;
                     } else {
-                        const float gi = g[a];
+                        const float gi = gi_v[ii];
                         U[a] = pcoef * gi * xi * (pw / n);
                         out[a] = gi * pw;
                     }
@@ -216,7 +248,7 @@ static inline SimtGrid simt_grid(int64_t NP, int C) {
 static inline int dgamma_ksplit(int64_t NP, int C) {
     const int tiles = ((C + DG_T - 1) / DG_T) * ((C + 1 + DG_T - 1) / DG_T);
     int64_t ks = ((int64_t)sm_count() * 2 + tiles - 1) / tiles;
-    const int64_t max_ks = (NP + 1023) / 1024;  // at least 1024 pixels per split
+    const int64_t max_ks = (NP + 127) / 128;  // at least 128 pixels per split (small layers are latency-bound: spread them)
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
     return (int)ks;
