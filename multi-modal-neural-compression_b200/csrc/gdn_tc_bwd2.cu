@@ -137,6 +137,10 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     constexpr int KG = PARK ? 1 : KH;
     constexpr int W = (KH % 16 == 0 && !PARK) ? 16 : 8;  // columns per tcgen05.ld / st
     constexpr int W1 = PARK ? 8 : W;            // epilogue 1 is where the 128-register budget is tightest
+    // refill a stage during the next tile's MMA1 wait instead of at the end of its own tile.  Measured on B200: helps the
+    // single-group double-stage layers (GDN(64)@256^2 0.817 -> 0.783 ms), hurts two groups on three stages (the
+    // refilled tile is the OTHER group's next one and loses its head start: GDN(50)@256^2 0.527 -> 0.669 ms)
+    constexpr bool DEFER = (NGROUPS == 1 && NSTAGES == 2);
     constexpr uint32_t kcores = P >> 2;
     constexpr uint32_t GAMMA_HI = desc_hi(kcores * 128u, 0);  // K-major, no swizzle: SBO = one 8-row group of cores
     constexpr uint32_t PIX_HI = desc_hi(1024u, 2);            // K-major (K = pixel), 128-byte swizzle
@@ -169,7 +173,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
 #define MMNC_SOFF(base, j) (((base) ^ (uint32_t)(((j) & 7) << 4)) + (uint32_t)((((j) >> 3) << 10) + (((j) & 7) << 7)))
     uint32_t parity = 0;
     bool first = true;
-    int oi = one_i;
+    int oi = one_i, pending = -1;
 #pragma unroll 1
     for (int k = group; k < t.n_k; k += NGROUPS) {
         const int s = k % NSTAGES;
@@ -213,6 +217,13 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
             fence_after();
             mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0, 128), GAMMA_HI, IDESC);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+            // A refill that could not be issued at the end of the previous tile (its MMA3 had not retired yet) is
+            // issued here, while the whole group waits for MMA1 anyway.
+            if (DEFER && pending >= 0) {
+                mbar_wait_addr(fbar, (uint32_t)(((pending - group) / NGROUPS) & 1));
+                if (pending + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, pending + NSTAGES);
+                pending = -1;
+            }
         }
         mbar_wait_addr(mbar, parity);
         parity ^= 1;
@@ -294,12 +305,22 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         }
         // No barrier here: the next tile's first barrier (after its A fill) already orders every thread's TMEM reads
         // of this tile before the next MMA1 overwrites D, and A was last read by MMA2, which has completed.
-        // The stage is free once MMA3 (its last reader) has retired: refill it with the tile NSTAGES ahead.
+        // The stage is free once MMA3 (its last reader) has retired: refill it with the tile NSTAGES ahead, now or
+        // (DEFER) while the group waits for the next tile's MMA1.
         if (leader) {
-            mbar_wait_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1));
-            if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
+            if (DEFER) {
+                pending = k;
+            } else {
+                mbar_wait_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1));
+                if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
+            }
         }
         first = false;
+    }
+    // the last tile of the group: wait for its MMA3 (D3 is final after that) and hand its stage on if anyone needs it
+    if (DEFER && leader && pending >= 0) {
+        mbar_wait_addr(fbar, (uint32_t)(((pending - group) / NGROUPS) & 1));
+        if (pending + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, pending + NSTAGES);
     }
     // the leader has seen the last MMA3 retire; after this barrier D3 is final for the whole group
     fence_before();
@@ -598,15 +619,19 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, int, const GdnParams, float *, float *,
                             int, uint32_t);
     Kernel kernel = nullptr;
-#define MMNC_PICK(N, G, S) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, true> : (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, false>)
+    // threads per pixel: 2 everywhere by default; 4 (1024 threads, 64 registers each) can be tried on the two-group
+    // instances with MMNC_BWD2_TPP=4
+    static const int tpp_env = []() { const char *e = getenv("MMNC_BWD2_TPP"); return e ? atoi(e) : 0; }();
+    const int tpp = (geo.groups == 2 && tpp_env == 4) ? 4 : 2;
+#define MMNC_PICK(N, G, S, T) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, T, true> : (Kernel)gdn_tc_backward2_kernel<N, G, S, T, false>)
     const int key = (geo.P / 16) * 100 + geo.groups * 10 + geo.stages;
     switch (key) {
-        case 223: kernel = MMNC_PICK(2, 2, 3); break;
-        case 323: kernel = MMNC_PICK(3, 2, 3); break;
-        case 423: kernel = MMNC_PICK(4, 2, 3); break;
-        case 512: kernel = MMNC_PICK(5, 1, 2); break;
-        case 611: kernel = MMNC_PICK(6, 1, 1); break;
-        case 711: kernel = MMNC_PICK(7, 1, 1); break;
+        case 223: kernel = tpp == 4 ? MMNC_PICK(2, 2, 3, 4) : MMNC_PICK(2, 2, 3, 2); break;
+        case 323: kernel = tpp == 4 ? MMNC_PICK(3, 2, 3, 4) : MMNC_PICK(3, 2, 3, 2); break;
+        case 423: kernel = tpp == 4 ? MMNC_PICK(4, 2, 3, 4) : MMNC_PICK(4, 2, 3, 2); break;
+        case 512: kernel = MMNC_PICK(5, 1, 2, 2); break;
+        case 611: kernel = MMNC_PICK(6, 1, 1, 2); break;
+        case 711: kernel = MMNC_PICK(7, 1, 1, 2); break;
         default: break;
     }
 #undef MMNC_PICK
@@ -617,7 +642,7 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     }
     MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
     float *part = static_cast<float *>(workspace);
-    kernel<<<(unsigned)grid, geo.groups * 2 * 128, geo.smem, s>>>(tm_x, tm_g, (int)ntiles, (int)(HW / tcb2::TILE), (int)HW,
+    kernel<<<(unsigned)grid, geo.groups * tpp * 128, geo.smem, s>>>(tm_x, tm_g, (int)ntiles, (int)(HW / tcb2::TILE), (int)HW,
                                                                    prm, dx, part, (int)C, geo.tmem_cols);
     if (int rc = after_launch("gdn_tc_backward2_kernel")) return rc;
     return gdn_reduce_partials(part, ksplit, (int)C, prm, dgamma, dbeta, s);
