@@ -58,30 +58,45 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
     }
 }
 
+__device__ __forceinline__ bool mbar_test_addr(uint32_t addr, uint32_t parity) {  // non-blocking
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
 template <int NSTAGES>
 __device__ __forceinline__ void bwd2_issue_tile(const volatile Bwd2Ctx &t, int k) {
     const int s = k % NSTAGES;
     const uint32_t tile = blockIdx.x + (uint32_t)k * gridDim.x;  // < 2^31 tiles (checked on the host)
     const int b = (int)(tile / (uint32_t)t.tiles_per_img);
     const int hw0 = (int)(tile - (uint32_t)b * (uint32_t)t.tiles_per_img) * tcb2::TILE;
-    const uint32_t bar = t.full_bar0 + 8u * (uint32_t)s;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)t.C * 1024u)
-                 : "memory");  // 2 tensors x 4 boxes x C rows x 128 B
+    // two barriers per stage: the x boxes are issued first and complete on their own barrier, so that the A fill and
+    // MMA1 start while g (first needed in epilogue 1) is still landing
+    const uint32_t bar_x = t.full_bar0 + 16u * (uint32_t)s, bar_g = bar_x + 8u;
+    const uint32_t half_bytes = (uint32_t)t.C * 512u;  // 4 boxes x C rows x 128 B per tensor
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_x), "r"(half_bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_g), "r"(half_bytes) : "memory");
     const uint32_t R8 = (uint32_t)t.R8, buf_bytes = R8 * 4096u;
     const uint32_t ub = t.stage0 + (uint32_t)s * 2u * buf_bytes, xb = ub + buf_bytes;
     const uint64_t tmx = reinterpret_cast<uint64_t>(t.tm_x), tmg = reinterpret_cast<uint64_t>(t.tm_g);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const uint32_t o = (uint32_t)a * R8 * 1024u;
+    for (int a = 0; a < 4; ++a)
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(xb + o), "l"(tmx), "r"(hw0 + 32 * a), "r"(0), "r"(b), "r"(bar)
+            ::"r"(xb + (uint32_t)a * R8 * 1024u), "l"(tmx), "r"(hw0 + 32 * a), "r"(0), "r"(b), "r"(bar_x)
             : "memory");
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(ub + o), "l"(tmg), "r"(hw0 + 32 * a), "r"(0), "r"(b), "r"(bar)
+            ::"r"(ub + (uint32_t)a * R8 * 1024u), "l"(tmg), "r"(hw0 + 32 * a), "r"(0), "r"(b), "r"(bar_g)
             : "memory");
-    }
 }
 
 // compile-time unrolled MMA chains (every per-step offset is an immediate inside the asm block, see tc_ptx.cuh)
@@ -180,16 +195,13 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         const uint32_t buf_bytes = (uint32_t)t.R8 * 4096u;
         const uint32_t us = t.stage0 + (uint32_t)s * 2u * buf_bytes, xs = us + buf_bytes;
         const uint32_t uq = us + bq, xq = xs + bq;
-        mbar_wait_addr(t.full_bar0 + 8u * (uint32_t)s, (uint32_t)((k / NSTAGES) & 1));
-        // ---- this thread's channels of x (and g) out of the landing buffers (conflict-free: a warp reads one 128 B row)
+        const uint32_t bar_x = t.full_bar0 + 16u * (uint32_t)s, fpar = (uint32_t)((k / NSTAGES) & 1);
+        mbar_wait_addr(bar_x, fpar);
+        // ---- this thread's channels of x out of the landing buffer (conflict-free: a warp reads one 128 B row)
         float xv[KH], gv[KG];
         MMNC_FRESH_OI();
 #pragma unroll
-        for (int j = 0; j < KH; ++j) {
-            const bool real = MMNC_REAL(j);
-            xv[j] = real ? ld_shared_f32(MMNC_SOFF(xq, j)) : 0.f;
-            if constexpr (!PARK) gv[j] = real ? ld_shared_f32(MMNC_SOFF(uq, j)) : 0.f;
-        }
+        for (int j = 0; j < KH; ++j) xv[j] = MMNC_REAL(j) ? ld_shared_f32(MMNC_SOFF(xq, j)) : 0.f;
         // ---- x^2 -> A (TMEM) and back into the landing buffer (MMA3's B operand); padded channel C is the constant 1,
         //      whose shared-memory row was written once at start-up and is never touched by the TMA box (C rows)
 #pragma unroll
@@ -224,6 +236,13 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                 if (pending + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, pending + NSTAGES);
                 pending = -1;
             }
+        }
+        // g has had the A fill and the MMA1 issue to land behind x
+        mbar_wait_addr(bar_x + 8u, fpar);
+        if constexpr (!PARK) {
+            MMNC_FRESH_OI();
+#pragma unroll
+            for (int j = 0; j < KH; ++j) gv[j] = MMNC_REAL(j) ? ld_shared_f32(MMNC_SOFF(uq, j)) : 0.f;
         }
         mbar_wait_addr(mbar, parity);
         parity ^= 1;
@@ -281,6 +300,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         parity ^= 1;
         fence_after();
         // ---- epilogue 2: dx = g n^p + 2 x t
+        bool refilled = false;
         {
             const uint32_t tile = blockIdx.x + (uint32_t)k * gridDim.x;
             const uint32_t tpi = (uint32_t)t.tiles_per_img, sb = t.sb;
@@ -301,6 +321,12 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                     const float out = fmaf(2.f * xv[j0 + j], __uint_as_float(r[j]), f);
                     if (MMNC_REAL(j0 + j)) __stcs(chan_ptr(dxb, sb, j0 + j), out);
                 }
+                // single stage: the next tile's load can only start when MMA3 has retired, and every cycle until then
+                // is exposed - poll between the blocks of this epilogue instead of finishing it first
+                if (NSTAGES == 1 && leader && !refilled && mbar_test_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1))) {
+                    if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
+                    refilled = true;
+                }
             }
         }
         // No barrier here: the next tile's first barrier (after its A fill) already orders every thread's TMEM reads
@@ -310,7 +336,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         if (leader) {
             if (DEFER) {
                 pending = k;
-            } else {
+            } else if (!refilled) {
                 mbar_wait_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1));
                 if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
             }
@@ -343,7 +369,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     constexpr int TPG = 128 * TPP;
     constexpr int THREADS = NGROUPS * TPG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[NSTAGES];
+    __shared__ uint64_t full_bar[2 * NSTAGES];  // [stage][x, g]
     __shared__ uint64_t mma_bar[NGROUPS];
     __shared__ uint64_t free_bar[NGROUPS];
     __shared__ uint32_t tmem_base_s;
@@ -359,7 +385,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     __shared__ Bwd2Ctx ctx_s;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < 2 * NSTAGES; ++s) mbar_init(&full_bar[s], 1);
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&mma_bar[q], 1);
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&free_bar[q], 1);
         tma_prefetch_desc(&tm_x);
