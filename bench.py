@@ -517,6 +517,13 @@ def run_b200(args):
                        "l2_policy": "inputs larger than L2 (4.7 GB of GDN activations per step vs 126 MB L2)"},
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
         }
+        # whole-step view: algorithmic GDN traffic of one step (8 B forward + 12 B backward per element; the entropy
+        # models and distortion terms add < 1 %) over the measured step time, against the same measured peak
+        if "roofline" in extra:
+            step_bytes = 20.0 * harness.gdn_elems_per_image * B
+            pk = extra["roofline"]["peak"]
+            line["step_roofline"] = {"bound": "hbm", "achieved": step_bytes / t_rate / 1e9, "peak": pk, "unit": "GB/s",
+                                     "frac": step_bytes / t_rate / 1e9 / pk, "algorithmic_bytes_per_step": step_bytes}
         line.update(extra)
         if "cpu_baseline" not in line:
             line["cpu_baseline"] = None

@@ -227,7 +227,7 @@ gdn_reduce_kernel(const float *__restrict__ part, int ksplit, int C, const GdnPa
 int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &prm, float *dgamma, float *dbeta,
                         cudaStream_t s) {
     const int64_t n = (int64_t)C * (C + 1);
-    if (n >= 2048) gdn_reduce_kernel<32><<<(unsigned)((n + 31) / 32), 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
+    if (n >= 8192) gdn_reduce_kernel<32><<<(unsigned)((n + 31) / 32), 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
     else gdn_reduce_kernel<8><<<(unsigned)((n + 7) / 8), 256, 0, s>>>(part, ksplit, C, prm, dgamma, dbeta);
     return after_launch("gdn_reduce_kernel");
 }
