@@ -32,8 +32,7 @@ gc_forward_kernel(const float *__restrict__ y, const float *__restrict__ scales,
         offset += st[1];
         noise_mode = MMNC_QUANT_NOISE_PHILOX;
     }
-    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
-        const int64_t b = e / Ss, s = e - b * Ss;
+    auto element = [&](int64_t b, int64_t s) {
         const int64_t ai = (b * C + c) * Ss + s;
         const int64_t yi = bcast ? (b * C + c) : ai;
         const float yv = y[yi];
@@ -43,11 +42,25 @@ gc_forward_kernel(const float *__restrict__ y, const float *__restrict__ scales,
         else if (noise_mode == MMNC_QUANT_NOISE_PHILOX) v = yv + philox_uniform_centered(seed, (uint64_t)yi + offset);
         else if (noise_mode == MMNC_QUANT_NOISE_GIVEN) v = yv + noise[yi];
         else v = yv;
-        float l = gc_likelihood_d(v, m, scales[ai], scale_bound);
+        // fp32 without the erfc cancellation (hd_math.cuh): within 1e-6 of the float64 value of the same formula
+        float l = gc_likelihood_s(v, m, scales[ai], scale_bound);
         if (lik_bound > 0.f) l = max_nan(l, lik_bound);
         lik[ai] = l;
         if (!bcast || s == 0) y_hat[yi] = v;
         acc += logf(l);
+    };
+    if (n < (1ll << 31)) {  // 32-bit index arithmetic (a 64-bit division per element costs as much as the likelihood)
+        const uint32_t n32 = (uint32_t)n, ss32 = (uint32_t)Ss, step = gridDim.y * blockDim.x;
+        for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < n32; e += step) {
+            const uint32_t b = e / ss32;
+            element((int64_t)b, (int64_t)(e - b * ss32));
+            if (e + step < e) break;  // wrap-around guard
+        }
+    } else {
+        for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
+            const int64_t b = e / Ss;
+            element(b, e - b * Ss);
+        }
     }
     if (lnsum != nullptr) {
         const float tot = block_sum(acc, red);
@@ -79,7 +92,7 @@ gc_backward_kernel(const float *__restrict__ y_hat, const float *__restrict__ sc
             const float v = y_hat[yi];
             const float m = (means != nullptr) ? means[yi] : 0.f;
             const float sc = scales[ai];
-            const float raw = gc_likelihood(v, m, sc, scale_bound);
+            const float raw = gc_likelihood_s(v, m, sc, scale_bound);
             const float l = (lik_bound > 0.f) ? max_nan(raw, lik_bound) : raw;
             float g = (g_lik != nullptr ? g_lik[ai] : 0.f) + gls / l;
             if (lik_bound > 0.f) g = lower_bound_grad(raw, lik_bound, g);

@@ -21,12 +21,13 @@ void hc_eb_forward(const float *v, int C, int L, const float *params, float boun
         for (int k = 0; k < EB_NP; ++k) P[k] = eb_transform(k, params[c * EB_NP + k]);
         for (int i = 0; i < L; ++i) {
             const float t = v[c * L + i];
-            const float lo = eb_logits<false>(P, t - 0.5f, nullptr), up = eb_logits<false>(P, t + 0.5f, nullptr);
-            float l = eb_likelihood(lo, up, form);
+            const float tl = t - 0.5f, tu = t + 0.5f;
+            float l = eb_likelihood_s(P, tl, tu - tl);  // what the GPU forward evaluates (both forms are this number)
+            (void)form;
             if (bound > 0.f) l = max_nan(l, bound);
             lik[c * L + i] = l;
-            if (lower_out) lower_out[c * L + i] = lo;
-            if (upper_out) upper_out[c * L + i] = up;
+            if (lower_out) lower_out[c * L + i] = eb_logits<false>(P, tl, nullptr);
+            if (upper_out) upper_out[c * L + i] = eb_logits<false>(P, tu, nullptr);
         }
     }
 }
@@ -58,11 +59,28 @@ void hc_eb_backward(const float *v, int C, int L, const float *params, const flo
 void hc_gc_forward(const float *y_hat, const float *scales, int64_t n, float scale_bound, float lik_bound,
                    float *lik, float *d_y, float *d_sc) {
     for (int64_t i = 0; i < n; ++i) {
-        float l = gc_likelihood(y_hat[i], 0.f, scales[i], scale_bound);
+        float l = gc_likelihood_s(y_hat[i], 0.f, scales[i], scale_bound);  // what the GPU kernels evaluate
         if (lik_bound > 0.f) l = max_nan(l, lik_bound);
         lik[i] = l;
         gc_likelihood_grad(y_hat[i], 0.f, scales[i], scale_bound, &d_y[i], &d_sc[i]);
     }
+}
+
+// the stable fp32 EB likelihood the GPU forward uses (eb_likelihood_s), before the floor; params (C, 58) raw
+void hc_eb_likelihood_s(const float *v, int C, int L, const float *params, float *lik) {
+    for (int c = 0; c < C; ++c) {
+        float P[EB_NP];
+        for (int k = 0; k < EB_NP; ++k) P[k] = eb_transform(k, params[c * EB_NP + k]);
+        for (int i = 0; i < L; ++i) {
+            const float tl = v[c * L + i] - 0.5f, tu = v[c * L + i] + 0.5f;
+            lik[c * L + i] = eb_likelihood_s(P, tl, tu - tl);
+        }
+    }
+}
+
+// the stable fp32 likelihood the GPU forward uses (gc_likelihood_s), before the floor
+void hc_gc_likelihood_s(const float *y_hat, const float *scales, int64_t n, float scale_bound, float *lik) {
+    for (int64_t i = 0; i < n; ++i) lik[i] = gc_likelihood_s(y_hat[i], 0.f, scales[i], scale_bound);
 }
 
 void hc_scale_index(const float *scales, int64_t n, const float *table, int len, float bound, int32_t *idx) {
