@@ -133,46 +133,6 @@ MMNC_HD float eb_logits_backward(const float *P, float t, const EbTrace &tr, flo
     return dt;
 }
 
-// ---- float64 evaluation of the forward likelihood.
-// sigma(up) - sigma(lo) amplifies the rounding of the two logits by |logit| / (up - lo): measured on this path,
-// independent fp32 evaluations differ by up to 1.5e-5 relative, above north_star's 1e-5 bar.  The forward
-// kernel therefore evaluates the 5-layer MLP and the sigmoid difference in float64 (the tensors involved are
-// kilobytes at the reference's shapes) and rounds once to fp32; the backward pass stays in fp32.
-MMNC_HD double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
-MMNC_HD double eb_transform_d(int k, float raw) {
-    return eb_is_matrix(k) ? softplus_d((double)raw) : (eb_is_factor(k) ? tanh((double)raw) : (double)raw);
-}
-MMNC_HD double eb_logits_d(const double *P, double t) {
-    double h[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double a = P[i] * t + P[3 + i];
-        h[i] = a + P[6 + i] * tanh(a);
-    }
-#pragma unroll
-    for (int l = 1; l < 4; ++l) {
-        const int base = 9 + (l - 1) * 15;
-        double n[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double a = P[base + 3 * i] * h[0] + P[base + 3 * i + 1] * h[1] + P[base + 3 * i + 2] * h[2] + P[base + 9 + i];
-            n[i] = a + P[base + 12 + i] * tanh(a);
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) h[i] = n[i];
-    }
-    return P[54] * h[0] + P[55] * h[1] + P[56] * h[2] + P[57];
-}
-MMNC_HD double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
-MMNC_HD float eb_likelihood_d(double lower, double upper, int form) {
-    if (form == 0) {
-        const double sum = lower + upper;
-        const double s = (sum > 0.0) ? -1.0 : ((sum < 0.0) ? 1.0 : 0.0);
-        return (float)fabs(sigmoid_d(s * upper) - sigmoid_d(s * lower));
-    }
-    return (float)(sigmoid_d(upper) - sigmoid_d(lower));
-}
-
 // ---- fp32 evaluation of the forward likelihood WITHOUT the cancellation.
 // lik = sigma(F(t + 1/2)) - sigma(F(t - 1/2)) (the "sign" form of CompressAI is the same number, |sigma(s up) - sigma(s lo)|).
 // Instead of two independent logits, the lower logit F_l and the DIFFERENCE dF = F_u - F_l are carried through the five
@@ -274,23 +234,12 @@ MMNC_HD float gc_likelihood(float y_hat, float mean, float scale, float scale_bo
     const float lower = gc_std_cumulative((-0.5f - v) / sc);
     return upper - lower;
 }
-// float64 forward evaluation (same reasoning as eb_likelihood_d): Phi(a) - Phi(b) cancels, fp32 erfc pairs
-// differ by ~1e-5 relative between implementations.  The inputs (v, scale) and the two quotients are rounded to
-// fp32 exactly where torch rounds them; only erfc and the subtraction run in float64.
-MMNC_HD float gc_likelihood_d(float y_hat, float mean, float scale, float scale_bound) {
-    const float sc = max_nan(scale, scale_bound);
-    const float v = fabsf(y_hat - mean);
-    const float tu = (0.5f - v) / sc, tl = (-0.5f - v) / sc;
-    const float cu = GC_CONST * tu, cl = GC_CONST * tl;
-    const double upper = 0.5 * erfc((double)cu), lower = 0.5 * erfc((double)cl);
-    return (float)(upper - lower);
-}
 // fp32 evaluation WITHOUT the cancellation: lik = (1/sqrt(pi)) * integral of exp(-t^2) over [cu, cl], the two erfc
 // arguments torch computes (same fp32 roundings as above).  Narrow intervals (cl - cu < 0.5, i.e. scale > 1.41) are
 // integrated with a 5-point Gauss-Legendre rule: truncation error < 2e-9 relative where lik > 1e-3 and < 1e-6 down to
 // the 1e-9 floor, and every term is positive, so nothing cancels.  Wide intervals use the erfc difference, whose
 // cancellation factor is at most 1.9 there.  Holds the float64 bars of the parity tests (1e-5 bulk, 5e-5 tails) at
-// a fraction of the cost of two float64 erfc: the float64 version runs at 0.12 of the HBM roof at the roofline shape.
+// a fraction of the cost of two float64 erfc (the first build of this kernel: 0.12 of the HBM roof at the roofline shape).
 MMNC_HD float gc_likelihood_s(float y_hat, float mean, float scale, float scale_bound) {
     const float sc = max_nan(scale, scale_bound);
     const float v = fabsf(y_hat - mean);
