@@ -445,6 +445,31 @@ def test_gdn_backward_pipelined_long_sequences(shape):
         assert ((a - b).abs().max() / b.abs().max()).item() <= 2e-3
 
 
+
+def test_gdn_tma_kernels_fall_back_on_unaligned_or_odd_shapes():
+    """The TMA-fed kernels need 16-byte aligned tensors and H*W % 128 == 0; anything else must silently take the
+    first-generation kernels and give the same numbers."""
+    torch.manual_seed(23)
+    C, B, H, W = 50, 10, 64, 64
+    ours, _ = _pair_gdn(C, False, precision="tf32")
+    x_al = torch.randn(B, C, H, W, device=DEV)
+    x_un = torch.empty(B * C * H * W + 1, device=DEV)[1:].view(B, C, H, W)  # data pointer off by 4 bytes
+    x_un.copy_(x_al)
+    g = torch.randn(B, C, H, W, device=DEV)
+    assert x_un.data_ptr() % 16 != 0 and x_un.is_contiguous()
+    assert _gdn_bwd_variant(x_al, g) == 3 and _gdn_bwd_variant(x_un, g) == 2
+    outs = []
+    for x in (x_al, x_un):
+        xr = x.detach().requires_grad_(True)
+        y = ours(xr)
+        (gx,) = torch.autograd.grad(y, [xr], g)
+        outs.append((y.detach(), gx))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-6), "forward generations disagree"
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-4, atol=1e-5), "backward generations disagree"
+    odd = torch.randn(3, C, 30, 31, device=DEV)  # H*W = 930: no 128-pixel TMA tiles
+    assert _gdn_bwd_variant(odd, odd) == 2
+
+
 def test_gdn_reparam_lower_bound_gradient():
     """A.2 / A.5: below the bound the gradient passes only if it is negative."""
     C = 4
