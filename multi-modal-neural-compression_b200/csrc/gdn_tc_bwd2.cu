@@ -6,12 +6,20 @@
 //     128-byte swizzle).  A box lands as [channel][32 pixels] rows of 128 B in 1024-byte swizzle atoms, which IS the
 //     K-major (K = pixel) operand layout of the d gamma contraction: the threads square x / turn g into u IN PLACE, so
 //     the landing buffers double as the MMA3 operands and no second shared-memory copy exists.
-//   * NSTAGES landing stages are shared by NGROUPS compute groups of 256 threads; group q owns tiles q, q + NGROUPS, ...
-//     of the CTA's sequence and has its own TMEM accumulators (A/D and its own d gamma partial), its own MMA-issuing
-//     thread and its own mbarrier, so one group's epilogues overlap the other group's MMAs while the loads of the
-//     tiles after next are in flight.  The load of tile k + NSTAGES is issued by whichever group retires tile k's
-//     MMA3 (the last reader of that stage).
-//   * no global-load address arithmetic or load latency in the compute warps: registers hold x and g only.
+//   * NSTAGES landing stages are shared by NGROUPS compute groups of 256 threads (two threads per pixel = TMEM lane,
+//     each owning half of the channels); group q owns tiles q, q + NGROUPS, ... of the CTA's sequence and has its own
+//     TMEM columns (A, D, its own d gamma partial and - with two groups - a parking area for f = g n^p), its own
+//     MMA-issuing thread and its own mbarriers, so one group's epilogues overlap the other group's MMAs while the
+//     loads of the tiles after next are in flight.  C <= 63: 2 groups x 3 stages; C = 64 .. 79: 1 x 2; wider: 1 x 1
+//     (gamma and gamma^T alone take 100 KB at C = 100).
+//   * barriers per stage: x and g complete separately (the A fill and MMA1 start when x has landed, g is first needed
+//     in epilogue 1); per group: MMA1 / MMA2 done (alternating phases of one mbarrier) and MMA3 done (the stage may
+//     be refilled, d gamma is current).  Epilogue 2 runs while MMA3 is still executing.  The refill of a stage is
+//     issued by the group that retired it: at the end of the tile, during the next tile's MMA1 wait (1 group x 2
+//     stages), or - single stage - as soon as polling between the blocks of epilogue 2 sees MMA3 retired.
+//   * no global-load address arithmetic or load latency in the compute warps; every loop invariant lives in shared
+//     memory, descriptors are assembled inside the MMA asm blocks: no spills (see Bwd2Ctx and tc_ptx.cuh for why
+//     that matters more than usual here).
 // Requires HW % 128 == 0 (a 128-pixel tile never straddles two images) and 16-byte aligned tensors; everything else
 // stays on gdn_tc_bwd.cu.
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
