@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 TASKS = ("rgb", "depth_euclidean", "normal")
 MODEL = dict(model_type=3, latent_channels=128, conv_channels=100, lmbda=1e-2)
+METRIC = "images/s rate-path fwd+bwd (256x256 CLEVR-shaped, 3 tasks)"
 WORKLOAD = "C2: MultiTaskDisjointLatentCompressor -m 3 -t rgb depth_euclidean normal -l 128 -c 100 --lmbda 1e-2, 256x256"
 
 
@@ -302,7 +303,10 @@ def run_reference(args):
     sample = (f"full training step (heads + backbone convs + rate path + both Adam optimizers) at batch {B} on "
               f"{torch.get_num_threads()} host threads; oracle = CPU restatement of CompressAI 1.2.4 (parity unpinned)")
     print(json.dumps({
-        "impl": "reference", "metric": "images/s (training step, 256x256, 3 tasks)", "value": v, "unit": "images/s",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s",
+        "what": "the reference's whole training step on the host cores (conv heads + backbone + rate path + both Adam "
+                "steps): the counterpart of the b200 arm's `e2e`; the rate path alone on the CPU is `cpu_baseline` of "
+                "the b200 arm's line",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "images_per_step": B},
@@ -507,7 +511,7 @@ def run_b200(args):
         dist.barrier()
     if rank == 0:
         line = {
-            "metric": "images/s rate-path fwd+bwd (256x256 CLEVR-shaped, 3 tasks)", "value": value, "unit": "images/s",
+            "metric": METRIC, "value": value, "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_rate * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images_per_gpu": B, "global_batch": B * world,
