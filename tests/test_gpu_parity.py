@@ -364,7 +364,8 @@ def test_gdn_backward_tensor_core(shape, inverse):
 # 128 -> 1 x 2 stages; C % 8 == 0 takes beta from shared memory, otherwise through the constant MMA column
 @pytest.mark.parametrize("shape", [(10, 50, 64, 64), (5, 100, 128, 64), (10, 64, 64, 64), (12, 20, 64, 64),
                                    (10, 40, 32, 128), (10, 33, 64, 64), (10, 104, 64, 64), (10, 128, 64, 64),
-                                   (20, 16, 16, 128)])
+                                   (20, 16, 16, 128), (300, 16, 8, 16), (1, 50, 128, 128), (3, 112, 16, 8),
+                                   (2, 77, 16, 16)])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_gdn_forward_tensor_core_tma(shape, inverse):
     """TMA-in / TMA-out tcgen05 forward (gdn_tc_fwd2.cu) against the oracle; single-pass TF32 tolerance 1e-3."""
@@ -393,7 +394,8 @@ def _gdn_bwd_variant(x, g, precision="tf32"):
 # 90 -> (96,1,1), 100 / 110 -> (112,1,1); 320-640 tiles on 148 CTAs: groups with 1, 2 and 0 tiles all occur
 @pytest.mark.parametrize("shape", [(10, 50, 64, 64), (5, 100, 128, 64), (10, 64, 64, 64), (12, 20, 64, 64),
                                    (10, 40, 32, 128), (10, 90, 64, 64), (10, 63, 64, 64), (10, 110, 64, 64),
-                                   (20, 16, 16, 128)])
+                                   (20, 16, 16, 128), (300, 16, 8, 16), (1, 50, 128, 128), (3, 111, 16, 8),
+                                   (2, 77, 16, 16)])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_gdn_backward_tensor_core_pipelined(shape, inverse):
     """TMA-fed, software-pipelined tcgen05 backward (gdn_tc_bwd2.cu) against the float64 oracle; same stated
