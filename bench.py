@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-rans", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the rate-path step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--serial-heads", action="store_true",
+                    help="run the task heads' GDN sites one after the other on one stream (default: one stream per task head)")
     ap.add_argument("--precision", default="auto", help="GDN contraction: auto | fp32 | tf32 | 3xtf32")
     return ap.parse_args()
 
@@ -98,7 +100,7 @@ class RatePathHarness:
     Shapes are read off the real model: a single B=1 forward with hooks records the input shape of every GDN /
     IGDN site and of the two entropy models."""
 
-    def __init__(self, mm, model, batch, device, torch):
+    def __init__(self, mm, model, batch, device, torch, concurrent_heads=True):
         self.mm, self.torch, self.model, self.B = mm, torch, model, batch
         sites, shapes = [], {}
         hooks = []
@@ -115,11 +117,21 @@ class RatePathHarness:
             h.remove()
         g = torch.Generator(device=device).manual_seed(21)
         rnd = lambda *s: torch.randn(*s, device=device, generator=g)  # noqa: E731
+        # The T task heads are independent networks (mtc.py:109-177): their GDN sites may run concurrently, one CUDA stream
+        # per head (the small layers launch 32-128 CTAs and leave most of the 148 SMs idle when serialised).
+        owner = {}
+        for key in ("input_heads", "output_heads"):
+            if key in model.model:
+                for ti, head in enumerate(model.model[key]):
+                    for m_ in head.modules():
+                        owner[id(m_)] = ti
+        self.n_streams = (max(owner.values()) + 1) if (owner and concurrent_heads) else 1
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(self.n_streams)] if self.n_streams > 1 else []
         self.sites = []
         for mod, shp in sites:
             shp = (batch,) + shp[1:]
-            self.sites.append((mod, rnd(*shp).requires_grad_(True), rnd(*shp)))
-        self.gdn_elems_per_image = sum(int(x[0].numel()) for _, x, _ in self.sites)
+            self.sites.append((mod, rnd(*shp).requires_grad_(True), rnd(*shp), owner.get(id(mod), 0) % self.n_streams))
+        self.gdn_elems_per_image = sum(int(x[0].numel()) for _, x, _, _ in self.sites)
         zs, ys, ss = [(batch,) + shapes[k][1:] for k in ("z", "y", "s")]
         self.z = (torch.distributions.Laplace(0.0, 2.0).sample(zs).to(device)).requires_grad_(True)
         self.scales = torch.exp(torch.empty(ss, device=device).uniform_(-3.0, 4.16, generator=g)).requires_grad_(True)
@@ -130,17 +142,31 @@ class RatePathHarness:
         # gradients of the rate-path parameters live in one flat bucket (exchanged when N > 1)
         self.eb_params = [p for n, p in self.eb.named_parameters() if n != "quantiles"]
         self.lv = list(model.loss_balancer.parameters())
-        self.params = [p for m, _, _ in self.sites for p in (m.beta, m.gamma)] + self.eb_params + self.lv
+        self.params = [p for m, _, _, _ in self.sites for p in (m.beta, m.gamma)] + self.eb_params + self.lv
         self.bucket = mm.FlatGradBucket(self.params)
         self.loss_inputs = [self.z, self.y, self.scales] + list(self.x_hat.values()) + self.eb_params + self.lv
 
     def step(self, dist=None, world=1):
         torch, mm = self.torch, self.mm
-        for mod, x, g in self.sites:          # K4: every GDN / IGDN site, forward + backward
+
+        def site(mod, x, g):                  # K4: one GDN / IGDN site, forward + backward
             y = mod(x)
             _, gb, gg = torch.autograd.grad(y, [x, mod.beta, mod.gamma], g)
             mod.beta.grad.copy_(gb)
             mod.gamma.grad.copy_(gg)
+
+        if self.n_streams > 1:                # fork: one stream per task head; join before the entropy models
+            main = torch.cuda.current_stream()
+            for st in self.streams:
+                st.wait_stream(main)
+            for mod, x, g, sid in self.sites:
+                with torch.cuda.stream(self.streams[sid]):
+                    site(mod, x, g)
+            for st in self.streams:
+                main.wait_stream(st)
+        else:
+            for mod, x, g, _ in self.sites:
+                site(mod, x, g)
         self.eb.train(), self.gc.train()
         mm.ops.noise_source.step()            # advance the device-side Philox stream (part of the captured graph)
         z_hat, z_lik = self.eb(self.z)        # K1 + K2
@@ -178,7 +204,7 @@ def roofline_of_gdn(torch, mm, harness, peak_gbs, peak_src, precision):
     big = sorted(harness.sites, key=lambda s: -s[1].numel())[:2]
     eff = []
     with torch.no_grad():
-        for mod, x, g in big:
+        for mod, x, g, _ in big:
             eff.append((mod.beta_reparam(mod.beta).clone(), mod.gamma_reparam(mod.gamma).clone(), x.detach(), g,
                         mod.inverse))
     x0 = eff[0][2]
@@ -421,7 +447,7 @@ def run_b200(args):
         return float(t.item())
 
     # -------- value: the hot path with inputs resident in HBM
-    harness = RatePathHarness(mm, model, B, device, torch)
+    harness = RatePathHarness(mm, model, B, device, torch, concurrent_heads=not args.serial_heads)
     mm.ops.noise_source.enable_device_state(device, seed=21)  # Philox (seed, offset) on the device: graph-safe
     run_step = lambda: harness.step(dist, world)  # noqa: E731
     graph = None
@@ -518,6 +544,7 @@ def run_b200(args):
                        "parallelism": f"dp{world}", "gdn_precision": args.precision,
                        "gdn_elements_per_image": harness.gdn_elems_per_image,
                        "launch": "eager" if args.no_graph else "CUDA graph replay of one captured step",
+                       "head_streams": harness.n_streams,
                        "l2_policy": "inputs larger than L2 (4.7 GB of GDN activations per step vs 126 MB L2)"},
             "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e,
         }

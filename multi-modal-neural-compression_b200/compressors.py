@@ -16,6 +16,8 @@ lmbda * rec + comp, and all their gradients) is ONE launch (`mmnc_rd_epilogue`).
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional, Sequence, Tuple, Union
 
 import torch
@@ -137,8 +139,39 @@ class MultiTaskCompressor(nn.Module):
         raise NotImplementedError()
 
     # ------------------------------------------------------------------ forward (mtc.py:200-221, 491-505)
+    # The T task heads are independent networks (mtc.py:109-177, 209-221): they run concurrently, one CUDA stream per
+    # head.  Their deep layers launch a few dozen CTAs each and would leave most of the 148 SMs idle one after the
+    # other (rate-path step 6.8 -> 5.9 ms, bench.py).  Autograd replays every backward op on its forward stream and
+    # synchronises the streams itself; outputs that cross back to the caller's stream are recorded there so that
+    # the caching allocator does not recycle them early.  `concurrent_heads = False` (or MMNC_SERIAL_HEADS=1) restores
+    # the reference's one-after-the-other order; the results are identical either way.
+    concurrent_heads: bool = os.environ.get("MMNC_SERIAL_HEADS", "0") != "1"
+
+    def _run_heads(self, fns):
+        """fns: one zero-argument callable per head, each returning a tensor.  -> list of results."""
+        first = next(self.parameters(), None)
+        if (not self.concurrent_heads or len(fns) < 2 or first is None or not first.is_cuda):
+            return [f() for f in fns]
+        dev = first.device
+        main = torch.cuda.current_stream(dev)
+        key = ("head_streams", str(dev))
+        if key not in self._cache or len(self._cache[key]) < len(fns):
+            self._cache[key] = [torch.cuda.Stream(device=dev) for _ in fns]
+        streams = self._cache[key][: len(fns)]
+        outs = []
+        for f, st in zip(fns, streams):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                outs.append(f())
+        for o, st in zip(outs, streams):
+            main.wait_stream(st)
+            o.record_stream(main)
+        return outs
+
     def forward_input_heads(self, batch) -> torch.Tensor:
-        return torch.concat([self.model["input_heads"][i](batch[t]) for i, t in enumerate(self.tasks)], dim=1)
+        heads = self.model["input_heads"]
+        return torch.concat(self._run_heads([(lambda i=i, t=t: heads[i](batch[t])) for i, t in enumerate(self.tasks)]),
+                            dim=1)
 
     def forward_output_heads(self, stacked_latent_values):
         raise NotImplementedError()
@@ -349,7 +382,9 @@ class MultiTaskMixedLatentCompressor(MultiTaskCompressor):
         return model
 
     def forward_output_heads(self, stacked_latent_values):
-        return {t: self.model["output_heads"][i](stacked_latent_values) for i, t in enumerate(self.tasks)}
+        heads = self.model["output_heads"]
+        outs = self._run_heads([(lambda i=i: heads[i](stacked_latent_values)) for i in range(len(self.tasks))])
+        return dict(zip(self.tasks, outs))
 
 
 class SingleTaskCompressor(MultiTaskMixedLatentCompressor):
@@ -421,8 +456,10 @@ class MultiTaskDisjointLatentCompressor(MultiTaskCompressor):
         return model
 
     def forward_output_heads(self, stacked_latent_values):
-        return {t: self.model["output_heads"][i](self._get_task_channels(stacked_latent_values, t))
-                for i, t in enumerate(self.tasks)}
+        heads = self.model["output_heads"]
+        outs = self._run_heads([(lambda i=i, t=t: heads[i](self._get_task_channels(stacked_latent_values, t)))
+                                for i, t in enumerate(self.tasks)])
+        return dict(zip(self.tasks, outs))
 
 
 class MultiTaskSharedLatentCompressor(MultiTaskDisjointLatentCompressor):
@@ -461,11 +498,14 @@ class MultiTaskSharedLatentCompressor(MultiTaskDisjointLatentCompressor):
     def forward_output_heads(self, stacked_latent_values):
         B, _, H, W = stacked_latent_values.shape
         shared = self._shared_channels(stacked_latent_values)
-        out = {}
-        for i, t in enumerate(self.tasks):
+        heads = self.model["output_heads"]
+
+        def run(i, t):
             own = self._get_task_channels(stacked_latent_values, t)
-            out[t] = self.model["output_heads"][i](torch.stack([own, shared], dim=1).reshape((B, -1, H, W)))
-        return out
+            return heads[i](torch.stack([own, shared], dim=1).reshape((B, -1, H, W)))
+
+        outs = self._run_heads([(lambda i=i, t=t: run(i, t)) for i, t in enumerate(self.tasks)])
+        return dict(zip(self.tasks, outs))
 
 
 def build_compressor(model_type: int, tasks: Sequence[str], latent_channels: int, conv_channels: int,
