@@ -119,19 +119,23 @@ class RatePathHarness:
         rnd = lambda *s: torch.randn(*s, device=device, generator=g)  # noqa: E731
         # The T task heads are independent networks (mtc.py:109-177): their GDN sites may run concurrently, one CUDA stream
         # per head (the small layers launch 32-128 CTAs and leave most of the 148 SMs idle when serialised).
-        owner = {}
-        for key in ("input_heads", "output_heads"):
+        # The step keeps the model's dependency structure: input heads (concurrent) -> backbone (alone) -> output heads
+        # (concurrent); the backward of a site runs right after its forward, in the same phase.
+        owner, phase_of = {}, {}
+        for ph, key in ((0, "input_heads"), (2, "output_heads")):
             if key in model.model:
                 for ti, head in enumerate(model.model[key]):
                     for m_ in head.modules():
                         owner[id(m_)] = ti
+                        phase_of[id(m_)] = ph
         self.n_streams = (max(owner.values()) + 1) if (owner and concurrent_heads) else 1
         self.streams = [torch.cuda.Stream(device=device) for _ in range(self.n_streams)] if self.n_streams > 1 else []
         self.sites = []
         for mod, shp in sites:
             shp = (batch,) + shp[1:]
-            self.sites.append((mod, rnd(*shp).requires_grad_(True), rnd(*shp), owner.get(id(mod), 0) % self.n_streams))
-        self.gdn_elems_per_image = sum(int(x[0].numel()) for _, x, _, _ in self.sites)
+            self.sites.append((mod, rnd(*shp).requires_grad_(True), rnd(*shp), owner.get(id(mod), 0) % self.n_streams,
+                               phase_of.get(id(mod), 1)))
+        self.gdn_elems_per_image = sum(int(s_[1][0].numel()) for s_ in self.sites)
         zs, ys, ss = [(batch,) + shapes[k][1:] for k in ("z", "y", "s")]
         self.z = (torch.distributions.Laplace(0.0, 2.0).sample(zs).to(device)).requires_grad_(True)
         self.scales = torch.exp(torch.empty(ss, device=device).uniform_(-3.0, 4.16, generator=g)).requires_grad_(True)
@@ -142,7 +146,7 @@ class RatePathHarness:
         # gradients of the rate-path parameters live in one flat bucket (exchanged when N > 1)
         self.eb_params = [p for n, p in self.eb.named_parameters() if n != "quantiles"]
         self.lv = list(model.loss_balancer.parameters())
-        self.params = [p for m, _, _, _ in self.sites for p in (m.beta, m.gamma)] + self.eb_params + self.lv
+        self.params = [p for s_ in self.sites for p in (s_[0].beta, s_[0].gamma)] + self.eb_params + self.lv
         self.bucket = mm.FlatGradBucket(self.params)
         self.loss_inputs = [self.z, self.y, self.scales] + list(self.x_hat.values()) + self.eb_params + self.lv
 
@@ -155,18 +159,20 @@ class RatePathHarness:
             mod.beta.grad.copy_(gb)
             mod.gamma.grad.copy_(gg)
 
-        if self.n_streams > 1:                # fork: one stream per task head; join before the entropy models
-            main = torch.cuda.current_stream()
-            for st in self.streams:
+        main = torch.cuda.current_stream()
+        for phase in (0, 1, 2):
+            todo = [s_ for s_ in self.sites if s_[4] == phase]
+            if phase == 1 or self.n_streams == 1:          # backbone (or serial mode): the caller's stream
+                for mod, x, g, _, _ in todo:
+                    site(mod, x, g)
+                continue
+            for st in self.streams:                        # fork: one stream per task head
                 st.wait_stream(main)
-            for mod, x, g, sid in self.sites:
+            for mod, x, g, sid, _ in todo:
                 with torch.cuda.stream(self.streams[sid]):
                     site(mod, x, g)
-            for st in self.streams:
+            for st in self.streams:                        # join before the next phase
                 main.wait_stream(st)
-        else:
-            for mod, x, g, _ in self.sites:
-                site(mod, x, g)
         self.eb.train(), self.gc.train()
         mm.ops.noise_source.step()            # advance the device-side Philox stream (part of the captured graph)
         z_hat, z_lik = self.eb(self.z)        # K1 + K2
@@ -204,7 +210,7 @@ def roofline_of_gdn(torch, mm, harness, peak_gbs, peak_src, precision):
     big = sorted(harness.sites, key=lambda s: -s[1].numel())[:2]
     eff = []
     with torch.no_grad():
-        for mod, x, g, _ in big:
+        for mod, x, g, _, _ in big:
             eff.append((mod.beta_reparam(mod.beta).clone(), mod.gamma_reparam(mod.gamma).clone(), x.detach(), g,
                         mod.inverse))
     x0 = eff[0][2]
