@@ -20,15 +20,21 @@ constexpr int GDN_CH = 16;   // output channels per chunk
 // MODE 0: forward            acc_i = sum_j gamma[i][j] x_j^2 ; y_i = x_i * (beta_i + acc_i)^(-+1/2)
 // MODE 1: backward, stage 1  same contraction; u_i = p g_i x_i n_i^(p-1) -> U ; dx_i = g_i n_i^p
 // MODE 2: backward, stage 2  acc_k = sum_i gamma[i][k] u_i ; dx_k += 2 x_k acc_k
-template <int MODE>
-__global__ void __launch_bounds__(GDN_TP)
+// JS > 1 (small, latency-bound layers): JS threads share a pixel and split the contraction index between them, so the
+// serial chain of dependent load rounds is JS times shorter; their partial sums meet in shared memory.
+template <int MODE, int JS>
+__global__ void __launch_bounds__(GDN_TP *JS)
 gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t NP, int C, int64_t HW,
                 const GdnParams prm, int inverse, float *out, float *U) {
-    extern __shared__ __align__(16) float W[];  // [C][GDN_CH]
+    extern __shared__ __align__(16) float W[];  // [C][GDN_CH] (+ [JS - 1][GDN_CH][GDN_TP] partial sums when JS > 1)
+    constexpr int THREADS = GDN_TP * JS;
     const int nchunks = (C + GDN_CH - 1) / GDN_CH;
     const float pcoef = inverse ? 0.5f : -0.5f;
+    const int px = threadIdx.x % GDN_TP, js = threadIdx.x / GDN_TP;
+    const int jn = (C + JS - 1) / JS, j_begin = js * jn, j_end = (j_begin + jn < C) ? j_begin + jn : C;
+    float *part = W + (size_t)C * GDN_CH;
     for (int64_t tile = blockIdx.x; tile * GDN_TP < NP; tile += gridDim.x) {
-        const int64_t P = tile * GDN_TP + threadIdx.x;
+        const int64_t P = tile * GDN_TP + px;
         const bool valid = P < NP;
         const int64_t b = valid ? P / HW : 0;
         const int64_t base = b * C * HW + (valid ? P - b * HW : 0);
@@ -38,11 +44,11 @@ gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_
             __syncthreads();
             // loads first (eight per thread in flight), then the re-parametrisation and the shared-memory stores:
             // one dependent L2 round trip per element made this staging loop the longest part of a small layer
-            for (int sbase = threadIdx.x; sbase < C * GDN_CH; sbase += GDN_TP * 8) {
+            for (int sbase = threadIdx.x; sbase < C * GDN_CH; sbase += THREADS * 8) {
                 float raw[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int idx = sbase + u * GDN_TP;
+                    const int idx = sbase + u * THREADS;
                     float v = 0.f;
                     if (idx < C * GDN_CH) {
                         if (MODE == 2) {  // W[i][kk] = gamma[i][i0 + kk]
@@ -57,7 +63,7 @@ gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int idx = sbase + u * GDN_TP;
+                    const int idx = sbase + u * THREADS;
                     if (idx >= C * GDN_CH) break;
                     if (MODE == 2) {
                         const int i = idx / GDN_CH, kk = idx - i * GDN_CH;
@@ -69,24 +75,39 @@ gdn_simt_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_
                 }
             }
             __syncthreads();
-            if (!valid) continue;
             float acc[GDN_CH];
 #pragma unroll
             for (int k = 0; k < GDN_CH; ++k) acc[k] = 0.f;
+            if (valid) {
 #pragma unroll 16
-            for (int j = 0; j < C; ++j) {
-                float v = xin[(int64_t)j * HW];
-                if (MODE != 2) v = v * v;
-                const float4 *w4 = reinterpret_cast<const float4 *>(W + j * GDN_CH);
+                for (int j = j_begin; j < j_end; ++j) {
+                    float v = xin[(int64_t)j * HW];
+                    if (MODE != 2) v = v * v;
+                    const float4 *w4 = reinterpret_cast<const float4 *>(W + j * GDN_CH);
 #pragma unroll
-                for (int q = 0; q < GDN_CH / 4; ++q) {
-                    const float4 w = w4[q];
-                    acc[4 * q + 0] += v * w.x;
-                    acc[4 * q + 1] += v * w.y;
-                    acc[4 * q + 2] += v * w.z;
-                    acc[4 * q + 3] += v * w.w;
+                    for (int q = 0; q < GDN_CH / 4; ++q) {
+                        const float4 w = w4[q];
+                        acc[4 * q + 0] += v * w.x;
+                        acc[4 * q + 1] += v * w.y;
+                        acc[4 * q + 2] += v * w.z;
+                        acc[4 * q + 3] += v * w.w;
+                    }
                 }
             }
+            if (JS > 1) {  // slices 1 .. JS-1 hand their partial sums to slice 0 (fixed order: deterministic)
+                if (js > 0) {
+#pragma unroll
+                    for (int k = 0; k < GDN_CH; ++k) part[((js - 1) * GDN_CH + k) * GDN_TP + px] = acc[k];
+                }
+                __syncthreads();
+                if (js == 0) {
+#pragma unroll
+                    for (int q = 1; q < JS; ++q)
+#pragma unroll
+                        for (int k = 0; k < GDN_CH; ++k) acc[k] += part[((q - 1) * GDN_CH + k) * GDN_TP + px];
+                }
+            }
+            if (!valid || js != 0) continue;
             float xi_v[GDN_CH], gi_v[GDN_CH], be_v[GDN_CH];
 #pragma unroll
             for (int ii = 0; ii < GDN_CH; ++ii) {  // every load of the epilogue in flight before the first use
@@ -254,16 +275,39 @@ static inline int dgamma_ksplit(int64_t NP, int C) {
     return (int)ks;
 }
 
+// few blocks (small layers): 4 or 2 threads per pixel split the contraction index, see the kernel.  Up to one block
+// per SM: 4 (512 threads); up to two per SM: 2 (two 256-thread blocks fit one SM's registers, so still a single wave).
+static inline int simt_slices(const SimtGrid &gr) {
+    const int64_t blocks = (int64_t)gr.tiles * gr.split;
+    return blocks <= sm_count() ? 4 : (blocks <= 2 * (int64_t)sm_count() ? 2 : 1);
+}
+
+template <int MODE, int JS>
+static int simt_launch_js(const SimtGrid &gr, size_t smem, const float *x, const float *g, int64_t NP, int C, int64_t HW,
+                          const GdnParams &prm, int inverse, float *out, float *U, cudaStream_t s, const char *what) {
+    smem += sizeof(float) * (size_t)(JS - 1) * GDN_CH * GDN_TP;
+    if (smem > 48 * 1024)
+        MMNC_CUDA(cudaFuncSetAttribute(gdn_simt_kernel<MODE, JS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gdn_simt_kernel<MODE, JS><<<dim3(gr.tiles, gr.split), GDN_TP * JS, smem, s>>>(x, g, NP, C, HW, prm, inverse, out, U);
+    return after_launch(what);
+}
+
+template <int MODE>
+static int simt_launch(const SimtGrid &gr, size_t smem, const float *x, const float *g, int64_t NP, int C, int64_t HW,
+                       const GdnParams &prm, int inverse, float *out, float *U, cudaStream_t s, const char *what) {
+    switch (simt_slices(gr)) {
+        case 4: return simt_launch_js<MODE, 4>(gr, smem, x, g, NP, C, HW, prm, inverse, out, U, s, what);
+        case 2: return simt_launch_js<MODE, 2>(gr, smem, x, g, NP, C, HW, prm, inverse, out, U, s, what);
+        default: return simt_launch_js<MODE, 1>(gr, smem, x, g, NP, C, HW, prm, inverse, out, U, s, what);
+    }
+}
+
 int gdn_simt_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, float *y,
                      cudaStream_t s) {
     const int64_t NP = B * HW;
     const SimtGrid gr = simt_grid(NP, (int)C);
     const size_t smem = sizeof(float) * (size_t)C * GDN_CH;
-    if (smem > 48 * 1024)
-        MMNC_CUDA(cudaFuncSetAttribute(gdn_simt_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gdn_simt_kernel<0><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, nullptr, NP, (int)C, HW, prm, inverse, y,
-                                                                     nullptr);
-    return after_launch("gdn_simt_kernel<fwd>");
+    return simt_launch<0>(gr, smem, x, nullptr, NP, (int)C, HW, prm, inverse, y, nullptr, s, "gdn_simt_kernel<fwd>");
 }
 
 size_t gdn_simt_backward_workspace(int64_t B, int64_t C, int64_t HW) {
@@ -281,14 +325,8 @@ int gdn_simt_backward(const float *x, const float *g, int64_t B, int64_t C, int6
     float *part = U + ((B * C * HW + 63) / 64) * 64;
     const SimtGrid gr = simt_grid(NP, (int)C);
     const size_t smem = sizeof(float) * (size_t)C * GDN_CH;
-    if (smem > 48 * 1024) {
-        MMNC_CUDA(cudaFuncSetAttribute(gdn_simt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MMNC_CUDA(cudaFuncSetAttribute(gdn_simt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
-    gdn_simt_kernel<1><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, g, NP, (int)C, HW, prm, inverse, dx, U);
-    if (int rc = after_launch("gdn_simt_kernel<bwd1>")) return rc;
-    gdn_simt_kernel<2><<<dim3(gr.tiles, gr.split), GDN_TP, smem, s>>>(x, g, NP, (int)C, HW, prm, inverse, dx, U);
-    if (int rc = after_launch("gdn_simt_kernel<bwd2>")) return rc;
+    if (int rc = simt_launch<1>(gr, smem, x, g, NP, (int)C, HW, prm, inverse, dx, U, s, "gdn_simt_kernel<bwd1>")) return rc;
+    if (int rc = simt_launch<2>(gr, smem, x, g, NP, (int)C, HW, prm, inverse, dx, U, s, "gdn_simt_kernel<bwd2>")) return rc;
     const int ks = dgamma_ksplit(NP, (int)C);
     int64_t kper = (NP + ks - 1) / ks;
     kper = (kper + DG_K - 1) / DG_K * DG_K;
