@@ -472,6 +472,45 @@ def test_gdn_tma_kernels_fall_back_on_unaligned_or_odd_shapes():
     assert _gdn_bwd_variant(odd, odd) == 2
 
 
+
+@pytest.mark.parametrize("shape", [(16, 50, 256, 256), (16, 100, 128, 128)])
+def test_gdn_tensor_core_full_size_properties(shape):
+    """The two largest layer shapes of BASELINE config C2 (batch 16 of its 64) through the TMA-fed tensor-core kernels:
+    size-independent properties, and torch's own fp32 ops on the same device as the reference."""
+    torch.manual_seed(29)
+    B, C, H, W = shape
+    ours, _ = _pair_gdn(C, False, precision="tf32")
+    beta, gamma = ours.beta_reparam(ours.beta).detach(), ours.gamma_reparam(ours.gamma).detach()
+    x = torch.randn(*shape, device=DEV)
+    g = torch.randn(*shape, device=DEV)
+    assert _gdn_bwd_variant(x, g) == 3
+
+    def run(xi, gi):
+        xr, br, gr = xi.clone().requires_grad_(True), beta.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
+        y = mm.ops.gdn(xr, br, gr, False, "tf32")
+        return (y.detach(),) + torch.autograd.grad(y, [xr, br, gr], gi)
+
+    y, dx, db, dg = run(x, g)
+    # (1) odd symmetry in x and in g, batch independence: exact (the same roundings happen in the same order)
+    y2, dx2, db2, dg2 = run(-x, g)
+    assert torch.equal(y2, -y) and torch.equal(dx2, dx) and torch.equal(db2, -db) and torch.equal(dg2, -dg)
+    y3, dx3, _, _ = run(x[3:5].contiguous(), g[3:5].contiguous())
+    assert torch.equal(y3, y[3:5]) and torch.equal(dx3, dx[3:5])
+    # (2) d gamma / d beta are sums over images: two halves of the batch add up to the whole
+    _, _, dba, dga = run(x[: B // 2].contiguous(), g[: B // 2].contiguous())
+    _, _, dbb, dgb = run(x[B // 2:].contiguous(), g[B // 2:].contiguous())
+    assert ((dga + dgb - dg).abs().max() / dg.abs().max()).item() < 1e-5
+    assert ((dba + dbb - db).abs().max() / db.abs().max()).item() < 1e-5
+    # (3) torch's fp32 ops (conv2d with TF32 off) on the same device
+    xr, br, gr = x.clone().requires_grad_(True), beta.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        want = xr * torch.rsqrt(torch.nn.functional.conv2d(xr * xr, gr.reshape(C, C, 1, 1), br))
+        wdx, wdb, wdg = torch.autograd.grad(want, [xr, br, gr], g)
+    assert torch.allclose(y, want.detach(), rtol=1e-3, atol=1e-4)
+    for got, ref in ((dx, wdx), (db, wdb), (dg, wdg)):
+        assert ((got - ref).abs().max() / ref.abs().max()).item() <= 2e-3
+
+
 def test_gdn_reparam_lower_bound_gradient():
     """A.2 / A.5: below the bound the gradient passes only if it is negative."""
     C = 4
