@@ -312,8 +312,17 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                 // canonical no-swizzle MN-major layout has 4 MN elements contiguous, 8 K rows 16 B apart, SBO between MN
                 // groups (= 128 B here) and LBO between 8-row K groups (= kcores * 128 B): LBO / SBO swapped w.r.t. MMA1,
                 // the "B is MN-major" bit set in the instruction descriptor, one LBO per K step.
-                mma_ts_chain_step<0, P / 8, (int)(kcores * 8)>(a_base + P, a_base, desc_lo(t.gamma0, kcores * 128u),
-                                                               desc_hi(128u, 0), IDESC | (1u << 16));
+                // variants 1..4 of (LBO, SBO, per-K-step advance): 1 = canonical (kcores*128, 128, LBO); 2 = (128, kcores*128,
+                // kcores*128); 3 = (kcores*128, 128, 256); 4 = (128, kcores*128, 256)
+                const int var = t.mn_major_b2;
+                const uint32_t big = kcores * 128u;
+                const uint32_t lbo = (var == 1 || var == 3) ? big : 128u, sbo = (var == 1 || var == 3) ? 128u : big;
+                const uint32_t step16 = ((var == 1 || var == 2) ? big : 256u) >> 4;
+                const uint64_t d0 = make_desc(t.gamma0, lbo, sbo, 0);
+#pragma unroll 1
+                for (int ks = 0; ks < P / 8; ++ks)
+                    mma_tf32_ts(a_base + P, a_base + (uint32_t)(ks * 8), d0 + (uint64_t)(step16 * (uint32_t)ks),
+                                IDESC | (1u << 16), ks > 0 ? 1u : 0u);
             } else {
                 mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0 + (uint32_t)(P * P * 4), 128), GAMMA_HI, IDESC);
             }
@@ -671,7 +680,7 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     if (int rc = make_map(&tm_g, g, B, C, HW)) return rc;
     using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, int, const GdnParams, float *, float *,
                             int, uint32_t, int);
-    static const int mn_env = []() { const char *e = getenv("MMNC_BWD2_MN"); return (e && atoi(e) == 1) ? 1 : 0; }();
+    static const int mn_env = []() { const char *e = getenv("MMNC_BWD2_MN"); return e ? atoi(e) : 0; }();
     Kernel kernel = nullptr;
     // threads per pixel: 2 everywhere by default; 4 (1024 threads, 64 registers each) can be tried on the two-group
     // instances with MMNC_BWD2_TPP=4

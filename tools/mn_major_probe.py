@@ -1,6 +1,6 @@
 """Reproducer for the MN-major B operand experiment of gdn_tc_bwd2.cu (MMNC_BWD2_MN=1): decomposes the kernel's dx into
 f + 2 x t and reports which hypothesis for t explains it (true t, t built from gamma without the transpose, t = 0).
-usage: MMNC_GDN_BWD=v2 MMNC_BWD2_MN=1 python tools/mn_major_probe.py     (without MMNC_BWD2_MN: the shipped path)"""
+usage: MMNC_GDN_BWD=v2 MMNC_BWD2_MN=1..4 python tools/mn_major_probe.py     (without MMNC_BWD2_MN: the shipped path)"""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 import mmnc_b200 as mm
