@@ -49,7 +49,6 @@ struct Bwd2Ctx {
     uint32_t gamma0;         // shared address of the gamma tile; gamma^T follows P * P * 4 bytes later
     uint32_t full_bar0, mma_bar0, free_bar0;  // shared addresses of the mbarrier arrays
     uint32_t tmem_base;
-    int mn_major_b2;         // experiment: MMA2 reads gamma itself as an MN-major operand instead of the gamma^T copy
     const void *tm_x, *tm_g;
     float *dx;
 };
@@ -114,14 +113,6 @@ __device__ __forceinline__ void mma_ts_chain(uint32_t d, uint32_t a, uint32_t b_
     if constexpr (KS < NK) {
         tc::mma_tf32_ts_step<KS * 8, KS * 16>(d, a, b_lo, b_hi, idesc, KS > 0 ? 1u : 0u);
         mma_ts_chain<KS + 1, NK>(d, a, b_lo, b_hi, idesc);
-    }
-}
-// same chain with the B operand advanced by STEP16 (16-byte units) per K step: an MN-major operand steps by its LBO
-template <int KS, int NK, int STEP16>
-__device__ __forceinline__ void mma_ts_chain_step(uint32_t d, uint32_t a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
-    if constexpr (KS < NK) {
-        tc::mma_tf32_ts_step<KS * 8, KS * STEP16>(d, a, b_lo, b_hi, idesc, KS > 0 ? 1u : 0u);
-        mma_ts_chain_step<KS + 1, NK, STEP16>(d, a, b_lo, b_hi, idesc);
     }
 }
 template <int KS>
@@ -307,25 +298,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         //      MMA3: D3 += u^T x2 (K = 128 pixels of this stage), committed to the "stage free" barrier
         if (leader) {
             fence_after();
-            if (t.mn_major_b2) {
-                // EXPERIMENT (MMNC_BWD2_MN=1): B2[n = k][K = i] = gamma[i][k] is the gamma tile itself read MN-major: the
-                // canonical no-swizzle MN-major layout has 4 MN elements contiguous, 8 K rows 16 B apart, SBO between MN
-                // groups (= 128 B here) and LBO between 8-row K groups (= kcores * 128 B): LBO / SBO swapped w.r.t. MMA1,
-                // the "B is MN-major" bit set in the instruction descriptor, one LBO per K step.
-                // variants 1..4 of (LBO, SBO, per-K-step advance): 1 = canonical (kcores*128, 128, LBO); 2 = (128, kcores*128,
-                // kcores*128); 3 = (kcores*128, 128, 256); 4 = (128, kcores*128, 256)
-                const int var = t.mn_major_b2;
-                const uint32_t big = kcores * 128u;
-                const uint32_t lbo = (var == 1 || var == 3) ? big : 128u, sbo = (var == 1 || var == 3) ? 128u : big;
-                const uint32_t step16 = ((var == 1 || var == 2) ? big : 256u) >> 4;
-                const uint64_t d0 = make_desc(t.gamma0, lbo, sbo, 0);
-#pragma unroll 1
-                for (int ks = 0; ks < P / 8; ++ks)
-                    mma_tf32_ts(a_base + P, a_base + (uint32_t)(ks * 8), d0 + (uint64_t)(step16 * (uint32_t)ks),
-                                IDESC | (1u << 16), ks > 0 ? 1u : 0u);
-            } else {
-                mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0 + (uint32_t)(P * P * 4), 128), GAMMA_HI, IDESC);
-            }
+            mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0 + (uint32_t)(P * P * 4), 128), GAMMA_HI, IDESC);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
             mma_ss_chain<0>(tmem_base + (uint32_t)(NGROUPS * 2 * P + group * P), desc_lo(us, 16), desc_lo(xs, 16), PIX_HI,
                             (uint32_t)t.R8 * 64u, IDESC, first ? 0u : 1u);
@@ -397,7 +370,7 @@ template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse>
 __global__ void __launch_bounds__(NGROUPS * TPP * 128, 1)
 gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                         int ntiles, int tiles_per_img, int HW, const GdnParams prm, float *__restrict__ dx,
-                        float *__restrict__ part, int C, uint32_t tmem_cols, int mn_major_b2) {
+                        float *__restrict__ part, int C, uint32_t tmem_cols) {
     using namespace tc;
     using namespace tcb2;
     constexpr int P = KH8 * 16;
@@ -436,7 +409,6 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         c.mma_bar0 = smem_u32(&mma_bar[0]);
         c.free_bar0 = smem_u32(&free_bar[0]);
         c.tmem_base = 0;  // read from tmem_base_s once the allocation is visible
-        c.mn_major_b2 = mn_major_b2;
         c.tm_x = &tm_x; c.tm_g = &tm_g;
         c.dx = dx;
         ctx_s = c;
@@ -679,8 +651,7 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     if (int rc = make_map(&tm_x, x, B, C, HW)) return rc;
     if (int rc = make_map(&tm_g, g, B, C, HW)) return rc;
     using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, int, const GdnParams, float *, float *,
-                            int, uint32_t, int);
-    static const int mn_env = []() { const char *e = getenv("MMNC_BWD2_MN"); return e ? atoi(e) : 0; }();
+                            int, uint32_t);
     Kernel kernel = nullptr;
     // threads per pixel: 2 everywhere by default; 4 (1024 threads, 64 registers each) can be tried on the two-group
     // instances with MMNC_BWD2_TPP=4
@@ -706,7 +677,7 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
     float *part = static_cast<float *>(workspace);
     kernel<<<(unsigned)grid, geo.groups * tpp * 128, geo.smem, s>>>(tm_x, tm_g, (int)ntiles, (int)(HW / tcb2::TILE), (int)HW,
-                                                                   prm, dx, part, (int)C, geo.tmem_cols, mn_env);
+                                                                   prm, dx, part, (int)C, geo.tmem_cols);
     if (int rc = after_launch("gdn_tc_backward2_kernel")) return rc;
     return gdn_reduce_partials(part, ksplit, (int)C, prm, dgamma, dbeta, s);
 }
