@@ -147,8 +147,9 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     constexpr int P = KH8 * 16;   // padded channel count
     // TPP threads share a pixel (a TMEM lane) and own contiguous channel ranges of KH channels: P / 2 each for two
     // threads; for four, P / 4 rounded up to 8 (the last thread's range then runs past P: those blocks are skipped).
-    // Measured on B200: four threads per pixel (with f parked in TMEM to fit 128 registers) is SLOWER on the wide,
-    // single-group layers (GDN(100)@128^2: 0.444 vs 0.390 ms), so every instance below uses two.
+    // Measured on B200: four threads per pixel is SLOWER - on the wide, single-group layers (with f parked in TMEM to
+    // fit 128 registers; GDN(100)@128^2: 0.444 vs 0.390 ms) and on the two-group ones (1024 threads x 64 registers;
+    // GDN(50)@256^2: 0.621 vs 0.539 ms) - so every instance uses two.
     constexpr int KH = (TPP == 2) ? P / 2 : (P / 4 + 7) / 8 * 8;
     constexpr int TPG = 128 * TPP;
     // first local channel that may be padding: with two threads only the last 16 channels of a thread (C > P - 16)
@@ -653,19 +654,18 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, int, const GdnParams, float *, float *,
                             int, uint32_t);
     Kernel kernel = nullptr;
-    // threads per pixel: 2 everywhere by default; 4 (1024 threads, 64 registers each) can be tried on the two-group
-    // instances with MMNC_BWD2_TPP=4
-    static const int tpp_env = []() { const char *e = getenv("MMNC_BWD2_TPP"); return e ? atoi(e) : 0; }();
-    const int tpp = (geo.groups == 2 && tpp_env == 4) ? 4 : 2;
-#define MMNC_PICK(N, G, S, T) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, T, true> : (Kernel)gdn_tc_backward2_kernel<N, G, S, T, false>)
+    // two threads per pixel everywhere: four (1024 threads x 64 registers on the two-group instances, 512 x 128 with f
+    // parked in TMEM on the single-group ones) was measured slower on every layer shape (see the kernel's comment)
+    const int tpp = 2;
+#define MMNC_PICK(N, G, S) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, true> : (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, false>)
     const int key = (geo.P / 16) * 100 + geo.groups * 10 + geo.stages;
     switch (key) {
-        case 223: kernel = tpp == 4 ? MMNC_PICK(2, 2, 3, 4) : MMNC_PICK(2, 2, 3, 2); break;
-        case 323: kernel = tpp == 4 ? MMNC_PICK(3, 2, 3, 4) : MMNC_PICK(3, 2, 3, 2); break;
-        case 423: kernel = tpp == 4 ? MMNC_PICK(4, 2, 3, 4) : MMNC_PICK(4, 2, 3, 2); break;
-        case 512: kernel = MMNC_PICK(5, 1, 2, 2); break;
-        case 611: kernel = MMNC_PICK(6, 1, 1, 2); break;
-        case 711: kernel = MMNC_PICK(7, 1, 1, 2); break;
+        case 223: kernel = MMNC_PICK(2, 2, 3); break;
+        case 323: kernel = MMNC_PICK(3, 2, 3); break;
+        case 423: kernel = MMNC_PICK(4, 2, 3); break;
+        case 512: kernel = MMNC_PICK(5, 1, 2); break;
+        case 611: kernel = MMNC_PICK(6, 1, 1); break;
+        case 711: kernel = MMNC_PICK(7, 1, 1); break;
         default: break;
     }
 #undef MMNC_PICK
