@@ -29,7 +29,7 @@ constexpr int TILE = 128;  // pixels per tile = TMEM lanes
 struct Fwd2Ctx {
     int C, n_k;              // channels, tiles of this CTA (all groups together)
     int tiles_per_img;
-    uint32_t stage0;         // shared address of group 0 / stage 0; stages are C * 512 bytes each
+    uint32_t stage0;         // shared address of group 0 / stage 0; stages are Kp * 512 bytes each (C rows + padding rows)
     uint32_t gamma0;         // shared address of the gamma tile
     uint32_t beta0;          // shared address of beta (Np floats)
     uint32_t full_bar0, mma_bar0;
@@ -87,7 +87,9 @@ gdn_tc_forward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     __shared__ uint32_t tmem_base_s;
     __shared__ Fwd2Ctx ctx_s;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t stage_bytes = (uint32_t)C * 512u;
+    // a stage holds Kp rows: the TMA box writes the first C, the padding rows are initialised once (0, and 1 in the row
+    // of the constant channel that picks up beta) so that the A fill needs neither predicates nor selects
+    const uint32_t stage_bytes = (uint32_t)Kp * 512u;
     float *Bs = reinterpret_cast<float *>(smem + (size_t)NGROUPS * NSTAGES * stage_bytes);
     float *beta_s = Bs + Np * Kp;
     const int warp = threadIdx.x >> 5;
@@ -114,6 +116,12 @@ gdn_tc_forward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         c.tm_x = &tm_x;
         c.tm_y = &tm_y;
         ctx_s = c;
+    }
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(NGROUPS * NSTAGES) * (uint32_t)(Kp - C) * 128u; i += THREADS) {
+        const uint32_t st = i / ((uint32_t)(Kp - C) * 128u), o = i - st * (uint32_t)(Kp - C) * 128u;
+        const int r = C + (int)(o >> 7);
+        reinterpret_cast<float *>(smem + (size_t)st * stage_bytes)[(size_t)r * 128 + (o & 127u)] =
+            (kBetaInMma && r == Kp - 1) ? 1.f : 0.f;
     }
     __syncthreads();
     const volatile Fwd2Ctx &t = ctx_s;
@@ -191,23 +199,20 @@ gdn_tc_forward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         fwd2_wait(fbar0 + 8u * (uint32_t)(kk % NSTAGES), (uint32_t)((kk / NSTAGES) & 1));
         // ---- A operand: x^2 -> tf32 -> TMEM (lane = pixel, column = channel); channels >= C are padding.
         //      Thread `sub` of the pixel owns the contiguous blocks [sub NB, sub NB + NB): its first channel is folded
-        //      into the bases, every other offset is an immediate, and the loads are predicated (not branched) so that
-        //      all of them are in flight before the first use.
+        //      into the bases, every other offset is an immediate, and the loads are unconditional (padding rows of the
+        //      stage hold 0 / 1) so that all of them are in flight before the first use.
         {
             constexpr int NB = (KP8 + SPLIT - 1) / SPLIT;
             const int cb = sub * NB * 8;
             const uint32_t xc = xs + (uint32_t)cb * 512u;
             float xv[NB * 8];
 #pragma unroll
-            for (int i = 0; i < NB * 8; ++i) xv[i] = (cb + i < C) ? ld_shared_f32(xc + (uint32_t)i * 512u) : 0.f;
+            for (int i = 0; i < NB * 8; ++i) xv[i] = ld_shared_f32(xc + (uint32_t)i * 512u);  // padding rows: 0 / 1
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
                 uint32_t v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[j] = to_tf32_fast(xv[i * 8 + j] * xv[i * 8 + j]);
-                    if (kBetaInMma && cb + i * 8 + j == Kp - 1) v[j] = 0x3f800000u;  // the constant column that picks up beta
-                }
+                for (int j = 0; j < 8; ++j) v[j] = to_tf32_fast(xv[i * 8 + j] * xv[i * 8 + j]);
                 if (SPLIT == 1 || cb + i * 8 < Kp) tmem_st8(a_base + lane_sel + (uint32_t)(cb + i * 8), v);
             }
         }
@@ -236,7 +241,7 @@ gdn_tc_forward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             const uint32_t xc = xs + (uint32_t)q * 512u;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                xq[j] = (q + j < C) ? ld_shared_f32(xc + (uint32_t)j * 512u) : 0.f;
+                xq[j] = ld_shared_f32(xc + (uint32_t)j * 512u);  // rows >= C: padding or the next buffer, never stored back
                 if (!kBetaInMma) bv[j] = ld_shared_f32(beta_a + (uint32_t)(q + j) * 4u);
             }
             tmem_ld_wait();
@@ -343,7 +348,16 @@ static bool fwd2_geometry(int64_t C, Fwd2Geometry *g) {
     uint32_t cols = 32;
     while ((int)cols < g->groups * (g->Kp + g->Np)) cols <<= 1;
     g->tmem_cols = cols;
-    g->smem = (size_t)g->groups * g->stages * (size_t)C * 512 + fwd2_gamma_bytes(kp8) + 1024;
+    // A sub-thread whose column range runs past Kp, and the epilogue's rows C .. Np-1, read a few rows beyond their
+    // stage - never used, but they must stay inside the allocation for the last stage too: gamma follows the stages,
+    // and a tail is added where gamma is smaller than the over-read.
+    const int split = fwd2_split(kp8);
+    const int nb = (kp8 + split - 1) / split;
+    const int last_row = (nb * 8 * split > g->Np) ? nb * 8 * split : g->Np;
+    const size_t over = (size_t)(last_row - g->Kp) * 512;
+    const size_t tail = over > fwd2_gamma_bytes(kp8) ? over - fwd2_gamma_bytes(kp8) : 0;
+    g->smem = (size_t)g->groups * g->stages * (size_t)g->Kp * 512 + fwd2_gamma_bytes(kp8) + tail + 1024;
+    if (g->smem + 512 > 227 * 1024) return false;
     return true;
 }
 
