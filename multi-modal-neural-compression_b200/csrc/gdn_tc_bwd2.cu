@@ -194,6 +194,11 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     // selects out of the tile loop, keeps them in registers for the whole kernel and spills them
 #define MMNC_REAL(j) ((j) < TAIL0 || (j) - TAIL0 < oi)
 #define MMNC_FRESH_OI() asm volatile("" : "+r"(oi))
+    // The landing buffers store 8 R8 >= C + 1 rows per K atom; rows >= C are never written by the TMA box and hold 0
+    // (row C of the x buffer: 1, the constant channel), so x and g are loaded and x^2 / u written back WITHOUT per-channel
+    // predicates or selects.  Only a thread's last 8-channel block can lie beyond the stored rows (P - 8 R8 is 0 or 8).
+    const bool last_ok = (c_begin + KH <= 8 * (int)t.R8);
+#define MMNC_ROW(j) ((j) < KH - 8 || last_ok)
 #define MMNC_SOFF(base, j) (((base) ^ (uint32_t)(((j) & 7) << 4)) + (uint32_t)((((j) >> 3) << 10) + (((j) & 7) << 7)))
     uint32_t parity = 0;
     bool first = true;
@@ -210,7 +215,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         float xv[KH], gv[KG];
         MMNC_FRESH_OI();
 #pragma unroll
-        for (int j = 0; j < KH; ++j) xv[j] = MMNC_REAL(j) ? ld_shared_f32(MMNC_SOFF(xq, j)) : 0.f;
+        for (int j = 0; j < KH; ++j) xv[j] = MMNC_ROW(j) ? ld_shared_f32(MMNC_SOFF(xq, j)) : 0.f;
         // ---- x^2 -> A (TMEM) and back into the landing buffer (MMA3's B operand); padded channel C is the constant 1,
         //      whose shared-memory row was written once at start-up and is never touched by the TMA box (C rows)
 #pragma unroll
@@ -220,12 +225,8 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 const uint32_t sq = to_tf32_fast(xv[j0 + j] * xv[j0 + j]);
-                if (MMNC_REAL(j0 + j)) {
-                    st_shared_u32(MMNC_SOFF(xq, j0 + j), sq);
-                    v[j] = sq;
-                } else {
-                    v[j] = (j0 + j - TAIL0 == oi) ? 0x3f800000u : 0u;
-                }
+                if (MMNC_ROW(j0 + j)) st_shared_u32(MMNC_SOFF(xq, j0 + j), sq);  // padding rows get their 0 / 1 back
+                v[j] = sq;
             }
             tmem_stw<W>(lane_a + j0, v);
         }
@@ -251,7 +252,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         if constexpr (!PARK) {
             MMNC_FRESH_OI();
 #pragma unroll
-            for (int j = 0; j < KH; ++j) gv[j] = MMNC_REAL(j) ? ld_shared_f32(MMNC_SOFF(uq, j)) : 0.f;
+            for (int j = 0; j < KH; ++j) gv[j] = MMNC_ROW(j) ? ld_shared_f32(MMNC_SOFF(uq, j)) : 0.f;
         }
         mbar_wait_addr(mbar, parity);
         parity ^= 1;
@@ -267,7 +268,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
 #pragma unroll
             for (int j = 0; j < W1; ++j) {
                 if constexpr (PARK)
-                    g8[j] = MMNC_REAL(j0 + j) ? ld_shared_f32(MMNC_SOFF(uq, j0 + j)) : 0.f;
+                    g8[j] = MMNC_ROW(j0 + j) ? ld_shared_f32(MMNC_SOFF(uq, j0 + j)) : 0.f;
                 else
                     g8[j] = gv[(j0 + j) % KG];
             }
@@ -281,12 +282,8 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                 const float u = (coef * g8[j]) * (xv[j0 + j] * pm1);
                 const float f = g8[j] * pw;
                 if constexpr (PARK) ff[j] = __float_as_uint(f); else gv[(j0 + j) % KG] = f;
-                if (MMNC_REAL(j0 + j)) {
-                    uu[j] = to_tf32_fast(u);
-                    st_shared_u32(MMNC_SOFF(uq, j0 + j), uu[j]);
-                } else {
-                    uu[j] = 0u;
-                }
+                uu[j] = to_tf32_fast(u);  // padding channels: g = 0 there, so u = 0
+                if (MMNC_ROW(j0 + j)) st_shared_u32(MMNC_SOFF(uq, j0 + j), uu[j]);
             }
             tmem_stw<W1>(lane_a + j0, uu);
             if constexpr (PARK) tmem_stw<W1>(lane_f + j0, ff);
@@ -362,6 +359,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     named_bar_sync(bar_id, TPG);
     fence_after();
 #undef MMNC_REAL
+#undef MMNC_ROW
 #undef MMNC_FRESH_OI
 #undef MMNC_SOFF
     return first;
