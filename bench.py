@@ -253,6 +253,41 @@ def roofline_of_gdn(torch, mm, harness, peak_gbs, peak_src, precision):
         "bound": "hbm", "kernel": "gdn forward (tcgen05), " + shape,
         "achieved": 8.0 * n / t_f / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": 8.0 * n / t_f / 1e9 / peak_gbs,
         "traffic": ncu_traffic[1], "algorithmic_bytes_per_launch": 8 * n, "launch_ms": t_f * 1e3}
+    # the other layer shapes of the step that move more than L2 holds, same measurement (fraction of the same peak)
+    others, seen = [], {tuple(x0.shape)}
+    for mod, x, g, _, _ in sorted(harness.sites, key=lambda s_: -s_[1].numel()):
+        shp = tuple(x.shape)
+        if shp in seen or x.numel() * 4 < 96e6:
+            continue
+        seen.add(shp)
+        with torch.no_grad():
+            b_, gm_ = mod.beta_reparam(mod.beta).clone(), mod.gamma_reparam(mod.gamma).clone()
+        xs_ = [x.detach(), torch.randn_like(x)]
+        Bq, Cq = shp[:2]
+        HWq = x.numel() // (Bq * Cq)
+        yq, dbq, dgq = torch.empty_like(x), torch.empty_like(b_), torch.empty_like(gm_)
+        nbq = int(L.mmnc_gdn_backward_workspace_bytes(Bq, Cq, HWq, prec))
+        wsq = torch.empty(nbq, dtype=torch.uint8, device=x.device)
+        k = [0]
+
+        def fq():
+            k[0] += 1
+            mm._lib.check(L.mmnc_gdn_forward(xs_[k[0] & 1].data_ptr(), Bq, Cq, HWq, b_.data_ptr(), gm_.data_ptr(),
+                                             int(mod.inverse), prec, yq.data_ptr(), st))
+
+        def bq():
+            k[0] += 1
+            mm._lib.check(L.mmnc_gdn_backward(xs_[k[0] & 1].data_ptr(), g.data_ptr(), Bq, Cq, HWq, b_.data_ptr(),
+                                              gm_.data_ptr(), int(mod.inverse), prec, yq.data_ptr(), dbq.data_ptr(),
+                                              dgq.data_ptr(), wsq.data_ptr(), nbq, st))
+
+        tf_, tb_ = time_kernel(torch, fq, reps=10), time_kernel(torch, bq, reps=10)
+        nq = x.numel()
+        others.append({"layer": "%sGDN(%d) on %dx%d, batch %d" % ("I" if mod.inverse else "", Cq, shp[2], shp[3], Bq),
+                       "forward_frac": 8.0 * nq / tf_ / 1e9 / peak_gbs, "forward_ms": tf_ * 1e3,
+                       "backward_frac": 12.0 * nq / tb_ / 1e9 / peak_gbs, "backward_ms": tb_ * 1e3})
+        del xs_, yq, wsq
+    out["roofline_other_layers"] = others
     return out
 
 
