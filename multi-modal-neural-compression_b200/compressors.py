@@ -38,6 +38,10 @@ task_parameters = {
 }
 
 
+# id(compressor) -> {key: value}: head streams and group tables (see MultiTaskCompressor._cache)
+_RUNTIME_CACHE: Dict[int, Dict[tuple, tuple]] = {}
+
+
 class DummyModule(nn.Module):
     """/root/reference/src/utils.py:56-61"""
 
@@ -94,7 +98,8 @@ class MultiTaskCompressor(nn.Module):
         self.kwargs = kwargs
         self.model: nn.ModuleDict = self._build_model()
         self.loss_balancer = UncertaintyWeightingStrategy(self.n_tasks)
-        self._cache: Dict[tuple, tuple] = {}
+        # per-instance switch (default from MMNC_SERIAL_HEADS at construction time); see _run_heads
+        self.concurrent_heads = os.environ.get("MMNC_SERIAL_HEADS", "0") != "1"
         self._optimizers = None
         self.grad_sync = None  # set by parallel.DataParallel: called between backward() and optimizer.step()
 
@@ -145,7 +150,14 @@ class MultiTaskCompressor(nn.Module):
     # synchronises the streams itself; outputs that cross back to the caller's stream are recorded there so that
     # the caching allocator does not recycle them early.  `concurrent_heads = False` (or MMNC_SERIAL_HEADS=1) restores
     # the reference's one-after-the-other order; the results are identical either way.
-    concurrent_heads: bool = os.environ.get("MMNC_SERIAL_HEADS", "0") != "1"
+    # CUDA streams and the small per-device lookup tables live in a module-level registry keyed by the compressor's
+    # id, NOT on the nn.Module: `copy.deepcopy(model)` / `torch.save(model)` must not meet stream handles.
+    @property
+    def _cache(self) -> Dict[tuple, tuple]:
+        return _RUNTIME_CACHE.setdefault(id(self), {})
+
+    def __del__(self):
+        _RUNTIME_CACHE.pop(id(self), None)
 
     def _run_heads(self, fns):
         """fns: one zero-argument callable per head, each returning a tensor.  -> list of results."""
@@ -281,7 +293,12 @@ class MultiTaskCompressor(nn.Module):
     def get_auxiliary_parameters(self):
         return [p for n, p in self.model.named_parameters() if n.endswith(".quantiles")]
 
-    def configure_optimizers(self, total_steps: int = 1000):
+    def configure_optimizers(self, total_steps: int):
+        """`total_steps` = the run's number of optimizer steps (the reference passes Lightning's
+        `estimated_stepping_batches`, mtc.py:405-409): required, because a cosine schedule with a guessed horizon
+        turns upwards again once the guess is passed."""
+        if int(total_steps) < 1:
+            raise ValueError("total_steps must be a positive number of optimizer steps")
         fused = next(self.parameters()).is_cuda
         main = torch.optim.Adam(self.get_main_parameters() + list(self.loss_balancer.parameters()),
                                 lr=self.learning_rate_main, fused=fused)
@@ -292,7 +309,7 @@ class MultiTaskCompressor(nn.Module):
 
     def optimizers(self):
         if self._optimizers is None:
-            self.configure_optimizers()
+            raise RuntimeError("call configure_optimizers(total_steps=...) before the first training_step")
         return self._optimizers[0], self._optimizers[1]
 
     def lr_schedulers(self):
@@ -324,7 +341,14 @@ class MultiTaskCompressor(nn.Module):
 
     @torch.no_grad()
     def validation_step(self, batch, batch_idx: int = 0):
-        return self._step(batch, is_train=False)
+        # Lightning calls model.eval() around validation (mtc.py:482-483 relies on it): quantisation must be round(),
+        # not additive noise, whatever mode the caller left the module in.  The previous mode is restored.
+        was_training = self.training
+        self.eval()
+        try:
+            return self._step(batch, is_train=False)
+        finally:
+            self.train(was_training)
 
     # ------------------------------------------------------------------ eval-time coding (mtc.py:486-549)
     def update_bottleneck_values(self):

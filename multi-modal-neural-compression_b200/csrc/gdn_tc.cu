@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "gdn_params.cuh"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace mmnc {
 
@@ -272,10 +273,9 @@ int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnPa
         set_error("gdn_tc_forward: no kernel instance for C = %lld", (long long)C);
         return MMNC_ERR_UNSUPPORTED;
     }
-    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // ask for the largest shared-memory carve-out: with the default heuristic the SM sometimes keeps a split that
-    // fits one CTA only, and the second co-resident CTA (the whole point of the TMEM budget) never lands
-    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // largest shared-memory carve-out: with the default heuristic the SM sometimes keeps a split that fits one CTA
+    // only, and the second co-resident CTA (the whole point of the TMEM budget) never lands
+    if (int rc = tmah::ensure_dynamic_smem(kernel, smem, true)) return rc;
     int64_t grid = (int64_t)sm_count() * (max_ctas < 4 ? max_ctas : 4);
     if (grid > tiles) grid = tiles;
     kernel<<<(unsigned)grid, tc::TILE_M, smem, s>>>(x, NP, HW, prm, inverse, y, g.C, g.Np, g.d_col, g.tmem_cols,

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "gdn_params.cuh"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace mmnc {
 
@@ -422,10 +423,9 @@ int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_
         set_error("gdn_tc_backward: no kernel instance for C = %lld", (long long)C);
         return MMNC_ERR_UNSUPPORTED;
     }
-    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // ask for the largest shared-memory carve-out: with the default heuristic the SM sometimes keeps a split that
-    // fits one CTA only, and the second co-resident CTA (the whole point of the TMEM budget) never lands
-    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // largest shared-memory carve-out: with the default heuristic the SM sometimes keeps a split that fits one CTA
+    // only, and the second co-resident CTA (the whole point of the TMEM budget) never lands
+    if (int rc = tmah::ensure_dynamic_smem(kernel, smem, true)) return rc;
     float *part = static_cast<float *>(workspace);
     kernel<<<(unsigned)grid, tcb::THREADS, smem, s>>>(x, g, NP, HW, prm, dx, part, (int)C, cols);
     if (int rc = after_launch("gdn_tc_backward_kernel")) return rc;

@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "gdn_params.cuh"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace mmnc {
 
@@ -507,24 +508,6 @@ int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &p
                         cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
 struct Bwd2Geometry {
     int P, groups, stages;
     uint32_t tmem_cols;
@@ -586,7 +569,7 @@ bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64
         B * C >= (1ll << 31))
         return false;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(g) & 15)) return false;
-    return encode_tiled() != nullptr;
+    return tmah::encode_tiled() != nullptr;
 }
 
 size_t gdn_tc_backward2_workspace(int64_t B, int64_t C, int64_t HW) {
@@ -596,40 +579,9 @@ size_t gdn_tc_backward2_workspace(int64_t B, int64_t C, int64_t HW) {
     return sizeof(float) * (size_t)sm_count() * geo.groups * C * (C + 1) + 256;
 }
 
-// cuTensorMapEncodeTiled is a driver-API call and wants a current context on the calling thread.  Runtime-API-only
-// threads (torch's autograd worker on device 0 never calls cudaSetDevice) may not have one bound yet.
-static void bind_primary_context() {
-    typedef CUresult (*GetCurrentFn)(CUcontext *);
-    static GetCurrentFn get_current = []() -> GetCurrentFn {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-        if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        return reinterpret_cast<GetCurrentFn>(p);
-    }();
-    CUcontext cur = nullptr;
-    if (get_current && get_current(&cur) == CUDA_SUCCESS && cur != nullptr) return;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);  // CUDA 12: initialises and binds the primary context
-    cudaGetLastError();
-}
-
 static int make_map(CUtensorMap *m, const float *p, int64_t B, int64_t C, int64_t HW) {
-    const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)C * HW * 4};
-    const cuuint32_t box[3] = {32, (cuuint32_t)C, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(p), dims, strides, box,
-                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("gdn_tc_backward2: cuTensorMapEncodeTiled failed (%d)", (int)r);
-        return MMNC_ERR_CUDA;
-    }
-    return MMNC_OK;
+    return tmah::tensor_map_3d(m, p, (uint64_t)HW, (uint64_t)C, (uint64_t)B, (uint64_t)HW * 4, (uint64_t)C * HW * 4, 32,
+                               (uint32_t)C, 1, CU_TENSOR_MAP_SWIZZLE_128B, "gdn_tc_backward2");
 }
 
 int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
@@ -646,7 +598,6 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     const int ksplit = (int)grid * geo.groups;
     MMNC_REQUIRE(workspace_bytes >= sizeof(float) * (size_t)ksplit * C * (C + 1), "gdn_backward: workspace too small");
     CUtensorMap tm_x, tm_g;
-    bind_primary_context();
     if (int rc = make_map(&tm_x, x, B, C, HW)) return rc;
     if (int rc = make_map(&tm_g, g, B, C, HW)) return rc;
     using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, int, const GdnParams, float *, float *,
@@ -672,7 +623,7 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
                   geo.groups, geo.stages);
         return MMNC_ERR_UNSUPPORTED;
     }
-    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
+    if (int rc = tmah::ensure_dynamic_smem(kernel, geo.smem)) return rc;
     float *part = static_cast<float *>(workspace);
     kernel<<<(unsigned)grid, geo.groups * tpp * 128, geo.smem, s>>>(tm_x, tm_g, (int)ntiles, (int)(HW / tcb2::TILE), (int)HW,
                                                                    prm, dx, part, (int)C, geo.tmem_cols);

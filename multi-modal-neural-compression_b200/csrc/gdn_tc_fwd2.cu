@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gdn_params.cuh"
 #include "tc_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace mmnc {
 
@@ -277,35 +278,6 @@ gdn_tc_forward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*Fwd2EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static void *fwd2_entry(const char *name) {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    return p;
-}
-
-static Fwd2EncodeFn fwd2_encode() {
-    static Fwd2EncodeFn fn = reinterpret_cast<Fwd2EncodeFn>(fwd2_entry("cuTensorMapEncodeTiled"));
-    return fn;
-}
-
-static void fwd2_bind_context() {  // see gdn_tc_bwd2.cu: driver-API calls want a current context on this thread
-    typedef CUresult (*GetCurrentFn)(CUcontext *);
-    static GetCurrentFn get_current = reinterpret_cast<GetCurrentFn>(fwd2_entry("cuCtxGetCurrent"));
-    CUcontext cur = nullptr;
-    if (get_current && get_current(&cur) == CUDA_SUCCESS && cur != nullptr) return;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
-    cudaGetLastError();
-}
-
 struct Fwd2Geometry {
     int Kp, Np, groups, stages, split;
     uint32_t tmem_cols;
@@ -378,22 +350,12 @@ bool gdn_tc_forward2_supported(const float *x, const float *y, int64_t B, int64_
     if (geo.stages < 3) return false;  // two-stage rings (C > 112) measured slower than gdn_tc.cu (0.53 vs 0.61 of the roof)
     if (HW % tcf2::TILE != 0 || HW >= (1 << 24) || B >= (1 << 24) || B * HW / tcf2::TILE >= (1ll << 31)) return false;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return false;
-    return fwd2_encode() != nullptr;
+    return tmah::encode_tiled() != nullptr;
 }
 
 static int fwd2_make_map(CUtensorMap *m, const float *p, int64_t B, int64_t C, int64_t HW) {
-    const cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)HW * 4, (cuuint64_t)C * HW * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)tcf2::TILE, (cuuint32_t)C, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = fwd2_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(p), dims, strides, box,
-                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("gdn_tc_forward2: cuTensorMapEncodeTiled failed (%d)", (int)r);
-        return MMNC_ERR_CUDA;
-    }
-    return MMNC_OK;
+    return tmah::tensor_map_3d(m, p, (uint64_t)HW, (uint64_t)C, (uint64_t)B, (uint64_t)HW * 4, (uint64_t)C * HW * 4,
+                               (uint32_t)tcf2::TILE, (uint32_t)C, 1, CU_TENSOR_MAP_SWIZZLE_NONE, "gdn_tc_forward2");
 }
 
 int gdn_tc_forward2(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, float *y,
@@ -407,7 +369,6 @@ int gdn_tc_forward2(const float *x, int64_t B, int64_t C, int64_t HW, const GdnP
     int64_t grid = sm_count();
     if (grid > ntiles) grid = ntiles;
     CUtensorMap tm_x, tm_y;
-    fwd2_bind_context();
     if (int rc = fwd2_make_map(&tm_x, x, B, C, HW)) return rc;
     if (int rc = fwd2_make_map(&tm_y, y, B, C, HW)) return rc;
     using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, const GdnParams, int, int, int, uint32_t);
@@ -430,7 +391,7 @@ int gdn_tc_forward2(const float *x, int64_t B, int64_t C, int64_t HW, const GdnP
         set_error("gdn_tc_forward2: no kernel instance for C = %lld", (long long)C);
         return MMNC_ERR_UNSUPPORTED;
     }
-    MMNC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)geo.smem));
+    if (int rc = tmah::ensure_dynamic_smem(kernel, geo.smem)) return rc;
     kernel<<<(unsigned)grid, geo.groups * split * 128, geo.smem, s>>>(tm_x, tm_y, (int)ntiles, (int)(HW / tcf2::TILE), prm,
                                                                    inverse, (int)C, geo.Np, geo.tmem_cols);
     return after_launch("gdn_tc_forward2_kernel");

@@ -131,3 +131,27 @@ def test_synthetic_batches_agree():
     a, b = mm.synthetic_batch(tasks, 2, size=32), orm.synthetic_batch(tasks, 2, size=32)
     assert all(torch.equal(a[t], b[t]) for t in tasks)
     assert a["semantic"].max() <= 16 and a["depth_euclidean"].max() <= 4.1
+
+
+def test_compressor_is_copyable_and_requires_an_optimizer_horizon():
+    """runtime handles (CUDA streams, group tables) live outside the nn.Module, so deepcopy / pickling of
+    the whole module keep working after use; `configure_optimizers` needs the run's step count."""
+    import copy
+    import pickle
+
+    m = mm.build_compressor(3, ("rgb", "depth_euclidean", "normal"), 14, 12)
+    m._cache[("probe", "cpu")] = (object(),)      # what a forward would leave behind
+    twin = copy.deepcopy(m)
+    assert twin._cache == {} and ("probe", "cpu") in m._cache
+    assert sorted(pickle.loads(pickle.dumps(m)).state_dict()) == sorted(m.state_dict())
+    assert "_cache" not in m.__dict__ and not any("stream" in k.lower() for k in m.__dict__)
+    with pytest.raises(RuntimeError, match="configure_optimizers"):
+        m.optimizers()
+    with pytest.raises(TypeError):
+        m.configure_optimizers()
+    with pytest.raises(ValueError):
+        m.configure_optimizers(total_steps=0)
+    m.configure_optimizers(total_steps=7)
+    assert m.lr_schedulers().T_max == 7
+    m.concurrent_heads = False
+    assert mm.build_compressor(1, ("mono",), 8, 8).concurrent_heads  # per-instance switch
