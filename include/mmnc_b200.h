@@ -174,6 +174,9 @@ int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int6
  * 0 = streaming (C <= 4), 1 = fp32 SIMT, 2 = fused tcgen05, 3 = fused tcgen05 fed by TMA and software-pipelined
  * (needs HW % 128 == 0 and 16-byte aligned x / g). */
 int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, int precision);
+/* Same for mmnc_gdn_forward: 0 = streaming, 1 = fp32 SIMT, 2 = tcgen05 (per-thread global loads), 3 = tcgen05 with
+ * TMA in / TMA out. */
+int mmnc_gdn_forward_variant(const float *x, const float *y, int64_t B, int64_t C, int64_t HW, int precision);
 /* Same two calls taking the RAW parameters of compressai.layers.GDN (`beta`, `gamma` as stored in the state dict):
  * the NonNegativeParametrizer re-parametrisation (effective = max(p, bound)^2 - pedestal) is applied while the
  * kernels stage the parameters, and the gradients come back w.r.t. the raw parameters with LowerBound's custom
@@ -212,28 +215,38 @@ int mmnc_build_indexes(const float *scales, int64_t n, const float *scale_table,
  *   Bit-exact with CompressAI's format: one 64-bit-state stream per image, 32-bit words, 16-bit probabilities,
  *   4-bit bypass escape, native-endian bytes.  One stream per row of `symbols`.
  *
+ *   Tables: mmnc_rans_pack_tables turns `_quantized_cdf` (n_cdfs, cdf_stride) int32 + `_cdf_length` into a RAGGED
+ *   uint16 table (row r = entries [row_start[r], row_start[r+1]) of `ragged`, values modulo 2^16: the final 65536 of
+ *   a row is stored as 0) that fits shared memory: 53 KB instead of 802 KB for the 64 x 3133 Gaussian table.  Call it
+ *   once per update(); ragged_capacity >= sum(cdf_sizes) rounded up to 8, 16-byte aligned; row_start has n_cdfs + 1
+ *   entries.
+ *
  *   symbols (n_streams, n_sym) int32; indexes same shape, or NULL with channel_period > 0 meaning
  *   index = (position / channel_period) % n_cdfs (EntropyBottleneck: channel id).
- *   cdf (n_cdfs, cdf_stride) int32 = `_quantized_cdf`; cdf_sizes = `_cdf_length`; offsets = `_offset`.
- *   encode: `staging` is scratch of n_streams*n_sym*8 bytes; `slabs` (n_streams, slab_words) uint32 with
- *   slab_words >= mmnc_rans_slab_words(n_sym); nbytes (n_streams) int32 receives each stream's byte count
+ *   cdf_sizes = `_cdf_length`; offsets = `_offset`.
+ *   encode: `staging` is scratch of n_streams*n_sym*12 bytes (16-byte aligned); `slabs` (n_streams, slab_words)
+ *   uint32 with slab_words >= mmnc_rans_slab_words(n_sym); nbytes (n_streams) int32 receives each stream's byte count
  *   (a negative value flags a malformed input for that stream).  The stream's bytes are the LAST nbytes[i]
- *   bytes of its slab.  mmnc_rans_compact packs them back to back: offsets (n_streams + 1) int64 exclusive
- *   scan, packed = concatenation.
+ *   bytes of its slab.  mmnc_rans_compact packs them back to back: meta = int64 offsets[n_streams + 1] (exclusive
+ *   scan) followed by int32 nbytes[n_streams] (so one device-to-host copy fetches both), packed = concatenation.
  * ------------------------------------------------------------------------------------------------------- */
 int64_t mmnc_rans_slab_words(int64_t n_sym);
+int mmnc_rans_pack_tables(const int32_t *cdf, const int32_t *cdf_sizes, int n_cdfs, int cdf_stride,
+                          int32_t *row_start, uint16_t *ragged, int64_t ragged_capacity, void *stream);
 int mmnc_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int64_t channel_period,
-                           int64_t n_streams, int64_t n_sym, const int32_t *cdf, int n_cdfs, int cdf_stride,
-                           const int32_t *cdf_sizes, const int32_t *offsets, void *staging, uint32_t *slabs,
-                           int64_t slab_words, int32_t *nbytes, void *stream);
+                           int64_t n_streams, int64_t n_sym, const uint16_t *ragged_cdf, int64_t ragged_len,
+                           const int32_t *row_start, const int32_t *cdf_sizes, const int32_t *offsets, int n_cdfs,
+                           void *staging, uint32_t *slabs, int64_t slab_words, int32_t *nbytes, void *stream);
 int mmnc_rans_compact(const uint32_t *slabs, int64_t slab_words, const int32_t *nbytes, int64_t n_streams,
-                      int64_t *offsets, uint8_t *packed, int64_t packed_capacity, void *stream);
-/* decode: packed bytes + offsets (n_streams + 1) as produced above (each stream 4-byte aligned is NOT
- * required).  status (n_streams) int32: 0 ok, negative = stream overrun / malformed. */
-int mmnc_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, const int32_t *indexes,
-                           int64_t channel_period, int64_t n_streams, int64_t n_sym, const int32_t *cdf,
-                           int n_cdfs, int cdf_stride, const int32_t *cdf_sizes, const int32_t *cdf_offsets,
-                           int32_t *symbols, int32_t *status, void *stream);
+                      int64_t *meta, uint8_t *packed, int64_t packed_capacity, void *stream);
+/* decode: stream i = lengths[i] bytes at packed + offsets[i]; every offset a multiple of 4 (pad between streams), a
+ * length that is not a whole number of 32-bit words is reported as corrupt.  status (n_streams) int32: 0 ok,
+ * negative = stream overrun / malformed. */
+int mmnc_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, const int32_t *lengths,
+                           const int32_t *indexes, int64_t channel_period, int64_t n_streams, int64_t n_sym,
+                           const uint16_t *ragged_cdf, int64_t ragged_len, const int32_t *row_start,
+                           const int32_t *cdf_sizes, const int32_t *cdf_offsets, int n_cdfs, int32_t *symbols,
+                           int32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ SIGNATURES = {
     "mmnc_gdn_backward_workspace_bytes": (ctypes.c_size_t, [I64, I64, I64, I32]),
     "mmnc_gdn_backward": (I32, [VP, VP, I64, I64, I64, VP, VP, I32, I32, VP, VP, VP, VP, ctypes.c_size_t, VP]),
     "mmnc_gdn_backward_variant": (I32, [VP, VP, I64, I64, I64, I32]),
+    "mmnc_gdn_forward_variant": (I32, [VP, VP, I64, I64, I64, I32]),
     "mmnc_gdn_forward_raw": (I32, [VP, I64, I64, I64, VP, VP, F32, F32, F32, I32, I32, VP, VP]),
     "mmnc_gdn_backward_raw": (I32, [VP, VP, I64, I64, I64, VP, VP, F32, F32, F32, I32, I32, VP, VP, VP, VP,
                                     ctypes.c_size_t, VP]),
@@ -61,9 +62,10 @@ SIGNATURES = {
     "mmnc_pmf_to_quantized_cdf_h": (I32, [ctypes.POINTER(ctypes.c_float), I32, I32, ctypes.POINTER(ctypes.c_uint32)]),
     "mmnc_build_indexes": (I32, [VP, I64, VP, I32, F32, VP, VP]),
     "mmnc_rans_slab_words": (I64, [I64]),
-    "mmnc_rans_encode_batch": (I32, [VP, VP, I64, I64, I64, VP, I32, I32, VP, VP, VP, VP, I64, VP, VP]),
+    "mmnc_rans_pack_tables": (I32, [VP, VP, I32, I32, VP, VP, I64, VP]),
+    "mmnc_rans_encode_batch": (I32, [VP, VP, I64, I64, I64, VP, I64, VP, VP, VP, I32, VP, VP, I64, VP, VP]),
     "mmnc_rans_compact": (I32, [VP, I64, VP, I64, VP, VP, I64, VP]),
-    "mmnc_rans_decode_batch": (I32, [VP, VP, VP, I64, I64, I64, VP, I32, I32, VP, VP, VP, VP, VP]),
+    "mmnc_rans_decode_batch": (I32, [VP, VP, VP, VP, I64, I64, I64, VP, I64, VP, VP, VP, I32, VP, VP, VP]),
 }
 
 

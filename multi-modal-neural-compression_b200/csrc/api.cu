@@ -49,6 +49,8 @@ int gdn_small_backward(const float *, const float *, int64_t, int64_t, int64_t, 
 // gdn_tc.cu
 bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision);
 int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, int, float *, cudaStream_t);
+// gdn_tc_fwd2.cu
+bool gdn_tc_forward2_supported(const float *x, const float *y, int64_t B, int64_t C, int64_t HW);
 // gdn_tc_bwd2.cu
 bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64_t C, int64_t HW);
 // gdn_tc_bwd.cu
@@ -115,6 +117,14 @@ extern "C" int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t
     if ((precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW))
         return gdn_tc_backward2_supported(x, g, B, C, HW) ? 3 : 2;
     return 1;
+}
+
+extern "C" int mmnc_gdn_forward_variant(const float *x, const float *y, int64_t B, int64_t C, int64_t HW,
+                                        int precision) {
+    if (gdn_small_supported(C)) return 0;
+    const int want = (precision == MMNC_GDN_AUTO) ? MMNC_GDN_TF32 : precision;
+    if (want == MMNC_GDN_FP32 || !gdn_tc_supported(B, C, HW, want)) return 1;
+    return (want == MMNC_GDN_TF32 && gdn_tc_forward2_supported(x, y, B, C, HW)) ? 3 : 2;
 }
 
 static int gdn_backward_impl(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,

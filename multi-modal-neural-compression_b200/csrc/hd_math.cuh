@@ -287,6 +287,40 @@ constexpr int RANS_PRECISION = 16;
 constexpr int RANS_BYPASS_BITS = 4;
 constexpr int RANS_BYPASS_MAX = 15;
 
+// Exact division of the coder state by a symbol frequency without a divide in the sequential loop.
+// For 1 < freq < 2^16 let s = ceil(log2 freq) and m = ceil(2^(63+s) / freq) (a 64-bit number, 2^63 <= m < 2^64).
+// Then floor(x / freq) == mulhi64(x, m) >> (s - 1) for every x < 2^63: x m / 2^(63+s) = x / freq + x e / (freq 2^(63+s))
+// with 0 <= e < freq, and the excess is below 1 / freq because x < 2^63 and freq <= 2^s.  The coder only divides states
+// below x_max = 2^47 freq <= 2^63.  m is computed where it is cheap (one thread per SYMBOL, pass 1); the exhaustive
+// host check over every freq lives in tests/test_kernel_math_hostcheck.py.
+MMNC_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+MMNC_HD int rans_ceil_log2(uint32_t freq) {  // freq >= 2
+#if defined(__CUDA_ARCH__)
+    return 32 - __clz((int)(freq - 1u));
+#else
+    int s = 0;
+    while ((1u << s) < freq) ++s;
+    return s;
+#endif
+}
+MMNC_HD uint64_t rans_reciprocal(uint32_t freq) {  // 1 < freq < 2^16; two 64-bit divides, no 128-bit arithmetic
+    const int s = rans_ceil_log2(freq);
+    const uint64_t n_hi = 1ull << (31 + s);          // 2^(63+s) = n_hi * 2^32
+    const uint64_t q_hi = n_hi / freq, r1 = n_hi - q_hi * freq;
+    const uint64_t n_lo = r1 << 32;                  // r1 < freq < 2^16
+    const uint64_t q_lo = n_lo / freq, r2 = n_lo - q_lo * freq;
+    return (q_hi << 32) + q_lo + (r2 != 0 ? 1ull : 0ull);
+}
+MMNC_HD uint64_t rans_div(uint64_t x, uint32_t freq, uint64_t m) {  // floor(x / freq), x < 2^63
+    return freq == 1u ? x : (mulhi64(x, m) >> (rans_ceil_log2(freq) - 1));
+}
+
 struct RansEnc {
     uint64_t x;
     uint32_t *ptr;  // write pointer, moves backwards
@@ -295,6 +329,13 @@ struct RansEnc {
         const uint64_t x_max = ((RANS_L >> RANS_PRECISION) << 32) * freq;
         if (x >= x_max) { *--ptr = (uint32_t)x; x >>= 32; }
         x = ((x / freq) << RANS_PRECISION) + (x % freq) + start;
+    }
+    // same update with the precomputed reciprocal of freq (rans_reciprocal): the kernels' sequential pass uses this
+    MMNC_HD void put_rcp(uint32_t start, uint32_t freq, uint64_t m) {
+        const uint64_t x_max = ((RANS_L >> RANS_PRECISION) << 32) * freq;
+        if (x >= x_max) { *--ptr = (uint32_t)x; x >>= 32; }
+        const uint64_t q = rans_div(x, freq, m);
+        x = (q << RANS_PRECISION) + (x - q * freq) + start;
     }
     MMNC_HD void put_bits(uint32_t val) {
         const uint64_t x_max = ((RANS_L >> 16) << 32) * (uint64_t)(1u << (16 - RANS_BYPASS_BITS));
@@ -370,6 +411,17 @@ struct RansDec {
         return (raw & 1u) ? (-value - 1) : (value + max_value);
     }
 };
+
+// Ragged 16-bit tables: a row of `len` CDF entries is stored as uint16 (the final entry 65536 wraps to 0 and is never
+// compared).  Slot = last s in [0, len - 2] with row[s] <= cum.
+MMNC_HD int rans_find_slot_u16(const uint16_t *row, int len, uint32_t cum) {
+    int lo = 0, hi = len - 1;  // first index in [0, len - 1) with row > cum; row[len - 1] stands for 65536 > cum
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((uint32_t)row[mid] > cum) hi = mid; else lo = mid + 1;
+    }
+    return lo - 1;
+}
 
 // s = (first position in cdf[0..len) with value > cum) - 1, by binary search (cdf strictly increasing)
 MMNC_HD int rans_find_slot(const int32_t *cdf, int len, uint32_t cum) {

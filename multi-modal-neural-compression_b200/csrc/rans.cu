@@ -5,18 +5,37 @@
 // decompress (reference call sites /root/reference/src/models/multi_task_compressor.py:509, 543, 546).
 //
 // The format is a single 64-bit rANS state per image stream, so the only parallelism is across streams:
-//   pass 1 (fully parallel, thread <-> symbol): symbol -> (cdf start, range, escape payload), written
-//           TRANSPOSED as staging[position][stream] so that pass 2 reads are coalesced across streams;
-//   pass 2 (thread <-> stream): walks positions last -> first, pushes words backwards into the stream's slab;
-//   compact: exclusive scan of byte counts + gather into one buffer, so the host does a single D2H.
-// Decoding is thread <-> stream with a binary search of the CDF row instead of CompressAI's linear scan.
+//   tables : the (n_cdfs x stride) int32 CDF table becomes a RAGGED uint16 table once per update() (53 KB for the
+//            64 x 3133 Gaussian table instead of 802 KB): small enough to live in shared memory;
+//   pass 1 (fully parallel, thread <-> symbol): symbol -> (cdf start : 16 | range : 16) and the exact 64-bit reciprocal
+//           of the range, written TRANSPOSED as [position][stream] so that pass 2 reads are coalesced across streams.
+//           The ragged table is staged in shared memory when the batch re-uses it often enough;
+//   pass 2 (thread <-> stream): walks positions last -> first; the state update is a multiply-high + shift instead of
+//           a 64-bit divide and modulo (hd_math.cuh: rans_div), 4 + 8 bytes read per symbol, escapes (rare) re-derive
+//           their payload from the symbol itself; words are pushed backwards into the stream's slab;
+//   compact: exclusive scan of byte counts + gather into one buffer, so the host does one D2H of metadata and one of
+//           bytes.
+// Decoding is thread <-> stream with the ragged table in shared memory and a binary search of the row (CompressAI
+// scans linearly), the stream words prefetched one ahead.
 #include "common.cuh"
 #include "hd_math.cuh"
+#include "tma_host.cuh"
 
 namespace mmnc {
 
 constexpr int RANS_MAP_THREADS = 256;
 constexpr int RANS_STREAM_THREADS = 32;
+constexpr int RANS_DECODE_THREADS = 128;
+constexpr size_t RANS_SMEM_TABLE_MAX = 200 * 1024;
+
+struct RansTables {
+    const uint16_t *ragged;     // concatenated rows, cdf values modulo 2^16
+    const int32_t *row_start;   // n_cdfs + 1 entries
+    const int32_t *sizes;       // entries per row (CompressAI's _cdf_length)
+    const int32_t *offsets;     // CompressAI's _offset
+    int n_cdfs;
+    int ragged_len;
+};
 
 __device__ __forceinline__ int32_t stream_index(const int32_t *indexes, int64_t channel_period, int n_cdfs,
                                                 int64_t stream, int64_t n_sym, int64_t pos) {
@@ -24,35 +43,79 @@ __device__ __forceinline__ int32_t stream_index(const int32_t *indexes, int64_t 
     return (int32_t)((pos / channel_period) % n_cdfs);
 }
 
-__global__ void __launch_bounds__(RANS_MAP_THREADS)
-rans_map_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t channel_period,
-                int64_t n_streams, int64_t n_sym, const int32_t *__restrict__ cdf, int n_cdfs, int cdf_stride,
-                const int32_t *__restrict__ cdf_sizes, const int32_t *__restrict__ offsets,
-                uint2 *__restrict__ staging, int32_t *__restrict__ nbytes) {
-    const int64_t total = n_streams * n_sym;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        // i enumerates (position, stream) with stream fastest so that the staging write is coalesced
-        const int64_t pos = i / n_streams, stream = i - pos * n_streams;
-        const int32_t ci = stream_index(indexes, channel_period, n_cdfs, stream, n_sym, pos);
-        uint2 e = make_uint2(0u, 0u);
-        if (ci < 0 || ci >= n_cdfs) {
-            nbytes[stream] = -1;  // malformed index: flag the stream (pass 2 keeps the flag)
-        } else {
-            const int32_t max_value = cdf_sizes[ci] - 2;
-            uint32_t raw;
-            const int slot = rans_map_symbol(symbols[stream * n_sym + pos], offsets[ci], max_value, &raw);
-            const int32_t *row = cdf + (int64_t)ci * cdf_stride;
-            const uint32_t start = (uint32_t)row[slot];
-            const uint32_t range = (uint32_t)(row[slot + 1] - row[slot]);
-            e = make_uint2((start & 0xFFFFu) | (range << 16), raw);
+// ---------------------------------------------------------------------------------------------- ragged tables
+__global__ void __launch_bounds__(256)
+rans_pack_tables_kernel(const int32_t *__restrict__ cdf, const int32_t *__restrict__ sizes, int n_cdfs, int stride,
+                        int32_t *__restrict__ row_start, uint16_t *__restrict__ ragged, int ragged_capacity) {
+    __shared__ int total_s;
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int r = 0; r < n_cdfs; ++r) {
+            row_start[r] = acc;
+            int len = sizes[r];
+            len = len < 0 ? 0 : (len > stride ? stride : len);
+            acc += len;
         }
-        staging[i] = e;
+        row_start[n_cdfs] = acc;
+        total_s = acc;
+    }
+    __syncthreads();
+    if (total_s > ragged_capacity) return;  // the host sized the buffer from the same lengths; defensive
+    for (int64_t i = threadIdx.x; i < (int64_t)n_cdfs * stride; i += blockDim.x) {
+        const int r = (int)(i / stride), c = (int)(i - (int64_t)r * stride);
+        if (c < sizes[r]) ragged[row_start[r] + c] = (uint16_t)((uint32_t)cdf[i] & 0xFFFFu);
     }
 }
 
+// ---------------------------------------------------------------------------------------------- encode, pass 1
+template <bool kSmemTable>
+__global__ void __launch_bounds__(RANS_MAP_THREADS)
+rans_map_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t channel_period,
+                int64_t n_streams, int64_t n_sym, const RansTables tb, uint32_t *__restrict__ stage_sr,
+                uint64_t *__restrict__ stage_rcp, int32_t *__restrict__ nbytes) {
+    extern __shared__ __align__(16) uint8_t rans_smem[];
+    const uint16_t *table = tb.ragged;
+    if (kSmemTable) {
+        // cooperative 16-byte copies (the ragged buffer is padded to a multiple of 8 entries by the host)
+        const uint4 *src = reinterpret_cast<const uint4 *>(tb.ragged);
+        uint4 *dst = reinterpret_cast<uint4 *>(rans_smem);
+        const int nvec = (tb.ragged_len + 7) >> 3;
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        table = reinterpret_cast<const uint16_t *>(rans_smem);
+    }
+    const int64_t total = n_streams * n_sym;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        // i enumerates (position, stream) with stream fastest so that the staging writes are coalesced
+        const int64_t pos = i / n_streams, stream = i - pos * n_streams;
+        const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
+        uint32_t sr = 0u;
+        uint64_t rcp = 0ull;
+        if (ci < 0 || ci >= tb.n_cdfs) {
+            nbytes[stream] = -1;  // malformed index: flag the stream (pass 2 keeps the flag)
+        } else {
+            const int32_t max_value = tb.sizes[ci] - 2;
+            uint32_t raw;
+            const int slot = rans_map_symbol(symbols[stream * n_sym + pos], tb.offsets[ci], max_value, &raw);
+            if (max_value >= 0) {
+                const uint16_t *row = table + tb.row_start[ci];
+                const uint32_t start = row[slot];
+                const uint32_t range = ((uint32_t)row[slot + 1] - start) & 0xFFFFu;  // the final 65536 is stored as 0
+                sr = start | (range << 16);
+                if (range > 1u) rcp = rans_reciprocal(range);
+            }
+        }
+        stage_sr[i] = sr;
+        stage_rcp[i] = rcp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- encode, pass 2
 __global__ void __launch_bounds__(RANS_STREAM_THREADS)
-rans_encode_kernel(const uint2 *__restrict__ staging, int64_t n_streams, int64_t n_sym, uint32_t *__restrict__ slabs,
+rans_encode_kernel(const uint32_t *__restrict__ stage_sr, const uint64_t *__restrict__ stage_rcp,
+                   const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t channel_period,
+                   int64_t n_streams, int64_t n_sym, const RansTables tb, uint32_t *__restrict__ slabs,
                    int64_t slab_words, int32_t *__restrict__ nbytes) {
     const int64_t stream = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (stream >= n_streams) return;
@@ -61,19 +124,34 @@ rans_encode_kernel(const uint2 *__restrict__ staging, int64_t n_streams, int64_t
     RansEnc enc;
     enc.init(slab + slab_words);
     bool ok = true;
-    for (int64_t pos = n_sym - 1; pos >= 0; --pos) {
-        const uint2 e = staging[pos * n_streams + stream];
-        const uint32_t start = e.x & 0xFFFFu, range = e.x >> 16;
+    // the staging reads do not depend on the coder state: keep the next entries in flight while the state chain runs
+    int64_t pos = n_sym - 1;
+    uint32_t sr_n = 0u;
+    uint64_t rcp_n = 0ull;
+    if (pos >= 0) { sr_n = stage_sr[pos * n_streams + stream]; rcp_n = stage_rcp[pos * n_streams + stream]; }
+    for (; pos >= 0; --pos) {
+        const uint32_t sr = sr_n;
+        const uint64_t rcp = rcp_n;
+        if (pos > 0) { sr_n = stage_sr[(pos - 1) * n_streams + stream]; rcp_n = stage_rcp[(pos - 1) * n_streams + stream]; }
+        const uint32_t start = sr & 0xFFFFu, range = sr >> 16;
         if (range == 0u || enc.ptr - slab < 16) { ok = false; break; }
-        if (start + range == 65536u) rans_put_escape_reversed(enc, e.y);  // the escape slot is the last one
-        enc.put(start, range);
+        if (start + range == 65536u) {
+            // the escape slot is the last one of its row; its payload is re-derived from the symbol (rare path)
+            const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
+            uint32_t raw;
+            rans_map_symbol(symbols[stream * n_sym + pos], tb.offsets[ci], tb.sizes[ci] - 2, &raw);
+            rans_put_escape_reversed(enc, raw);
+        }
+        enc.put_rcp(start, range, rcp);
     }
     if (!ok) { nbytes[stream] = -2; return; }
     enc.flush();
     nbytes[stream] = (int32_t)((slab + slab_words - enc.ptr) * (int64_t)sizeof(uint32_t));
 }
 
-// exclusive scan of max(nbytes, 0) into offsets[0..n]; single block of 1024 threads, chunked
+// exclusive scan of max(nbytes, 0) into offsets[0..n]; single block of 1024 threads, chunked.  The per-stream byte
+// counts / status codes are copied behind the offsets (meta = int64 offsets[n + 1] | int32 nbytes[n]) so that the host
+// fetches everything it needs to size the second copy with ONE device-to-host transfer.
 __global__ void __launch_bounds__(1024)
 rans_scan_kernel(const int32_t *__restrict__ nbytes, int64_t n, int64_t *__restrict__ offsets) {
     __shared__ int64_t warp_excl[32];
@@ -81,10 +159,13 @@ rans_scan_kernel(const int32_t *__restrict__ nbytes, int64_t n, int64_t *__restr
     __shared__ int64_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
+    int32_t *status_out = reinterpret_cast<int32_t *>(offsets + n + 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t base = 0; base < n; base += blockDim.x) {
         const int64_t i = base + threadIdx.x;
-        const int64_t v = (i < n && nbytes[i] > 0) ? (int64_t)nbytes[i] : 0;
+        const int32_t nb = (i < n) ? nbytes[i] : 0;
+        if (i < n) status_out[i] = nb;
+        const int64_t v = nb > 0 ? (int64_t)nb : 0;
         int64_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -114,10 +195,13 @@ rans_scan_kernel(const int32_t *__restrict__ nbytes, int64_t n, int64_t *__restr
     if (threadIdx.x == 0) offsets[n] = carry_s;
 }
 
+// one warp per stream, four streams per block
 __global__ void __launch_bounds__(128)
 rans_gather_kernel(const uint32_t *__restrict__ slabs, int64_t slab_words, const int32_t *__restrict__ nbytes,
-                   const int64_t *__restrict__ offsets, uint8_t *__restrict__ packed, int64_t capacity) {
-    const int64_t stream = blockIdx.x;
+                   const int64_t *__restrict__ offsets, int64_t n_streams, uint8_t *__restrict__ packed,
+                   int64_t capacity) {
+    const int64_t stream = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;
     const int32_t nb = nbytes[stream];
     if (nb <= 0) return;
     const int64_t off = offsets[stream];
@@ -125,38 +209,101 @@ rans_gather_kernel(const uint32_t *__restrict__ slabs, int64_t slab_words, const
     const int64_t words = nb >> 2;
     const uint32_t *src = slabs + stream * slab_words + (slab_words - words);
     uint32_t *dst = reinterpret_cast<uint32_t *>(packed + off);  // offsets are multiples of 4, packed is aligned
-    for (int64_t w = threadIdx.x; w < words; w += blockDim.x) dst[w] = src[w];
+    for (int64_t w = threadIdx.x & 31; w < words; w += 32) dst[w] = src[w];
 }
 
-__global__ void __launch_bounds__(RANS_STREAM_THREADS)
+// ---------------------------------------------------------------------------------------------- decode
+// The stream bytes are whole 32-bit words at 4-byte aligned offsets (the host pads); one word is always prefetched.
+struct RansDecW {
+    uint64_t x;
+    const uint32_t *p, *end;
+    uint32_t next;
+    bool overrun;
+    __device__ __forceinline__ uint32_t word() {
+        const uint32_t w = next;
+        if (p >= end) { overrun = true; return 0u; }
+        ++p;
+        next = (p < end) ? *p : 0u;
+        return w;
+    }
+    __device__ __forceinline__ void init(const uint32_t *begin, const uint32_t *end_) {
+        p = begin; end = end_; overrun = false;
+        next = (p < end) ? *p : 0u;
+        const uint64_t lo = word();
+        const uint64_t hi = word();
+        x = lo | (hi << 32);
+    }
+    __device__ __forceinline__ uint32_t peek() const { return (uint32_t)(x & 0xFFFFu); }
+    __device__ __forceinline__ void advance(uint32_t start, uint32_t freq) {
+        x = (uint64_t)freq * (x >> RANS_PRECISION) + (x & 0xFFFFu) - start;
+        if (x < RANS_L) x = (x << 32) | word();
+    }
+    __device__ __forceinline__ uint32_t get_bits() {
+        const uint32_t val = (uint32_t)(x & RANS_BYPASS_MAX);
+        x >>= RANS_BYPASS_BITS;
+        if (x < RANS_L) x = (x << 32) | word();
+        return val;
+    }
+    __device__ __forceinline__ int32_t get_escape(int32_t max_value) {
+        int32_t val = (int32_t)get_bits();
+        int32_t nb = val;
+        while (val == RANS_BYPASS_MAX && !overrun) { val = (int32_t)get_bits(); nb += val; }
+        uint32_t raw = 0;
+        for (int j = 0; j < nb && j < 8; ++j) raw |= get_bits() << (j * RANS_BYPASS_BITS);
+        const int32_t value = (int32_t)(raw >> 1);
+        return (raw & 1u) ? (-value - 1) : (value + max_value);
+    }
+};
+
+template <bool kSmemTable>
+__global__ void __launch_bounds__(RANS_DECODE_THREADS)
 rans_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restrict__ offsets,
-                   const int32_t *__restrict__ indexes, int64_t channel_period, int64_t n_streams, int64_t n_sym,
-                   const int32_t *__restrict__ cdf, int n_cdfs, int cdf_stride, const int32_t *__restrict__ cdf_sizes,
-                   const int32_t *__restrict__ cdf_offsets, int32_t *__restrict__ symbols,
+                   const int32_t *__restrict__ lengths, const int32_t *__restrict__ indexes, int64_t channel_period,
+                   int64_t n_streams, int64_t n_sym, const RansTables tb, int32_t *__restrict__ symbols,
                    int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) uint8_t rans_smem[];
+    const uint16_t *table = tb.ragged;
+    if (kSmemTable) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tb.ragged);
+        uint4 *dst = reinterpret_cast<uint4 *>(rans_smem);
+        const int nvec = (tb.ragged_len + 7) >> 3;
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        table = reinterpret_cast<const uint16_t *>(rans_smem);
+    }
     const int64_t stream = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (stream >= n_streams) return;
-    const int64_t b0 = offsets[stream], b1 = offsets[stream + 1];
+    const int64_t b0 = offsets[stream];
+    const int32_t len_bytes = lengths[stream];
     int32_t st = 0;
-    if (b1 - b0 < 8) { status[stream] = -1; return; }
-    RansDec dec;
-    dec.init(packed + b0, packed + b1);
+    if (len_bytes < 8 || (len_bytes & 3)) { status[stream] = -1; return; }
+    RansDecW dec;
+    dec.init(reinterpret_cast<const uint32_t *>(packed + b0), reinterpret_cast<const uint32_t *>(packed + b0 + len_bytes));
     for (int64_t pos = 0; pos < n_sym; ++pos) {
-        const int32_t ci = stream_index(indexes, channel_period, n_cdfs, stream, n_sym, pos);
-        if (ci < 0 || ci >= n_cdfs) { st = -3; break; }
-        const int32_t *row = cdf + (int64_t)ci * cdf_stride;
-        const int32_t len = cdf_sizes[ci];
+        const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
+        if (ci < 0 || ci >= tb.n_cdfs) { st = -3; break; }
+        const int32_t len = tb.sizes[ci];
         const int32_t max_value = len - 2;
-        const int slot = rans_find_slot(row, len, dec.peek());
+        if (max_value < 0) { st = -4; break; }
+        const uint16_t *row = table + tb.row_start[ci];
+        const int slot = rans_find_slot_u16(row, len, dec.peek());
         if (slot < 0 || slot > max_value) { st = -4; break; }
-        const uint32_t start = (uint32_t)row[slot];
-        dec.advance(start, (uint32_t)(row[slot + 1] - row[slot]));
+        const uint32_t start = row[slot];
+        dec.advance(start, ((uint32_t)row[slot + 1] - start) & 0xFFFFu);
         int32_t value = slot;
         if (slot == max_value) value = dec.get_escape(max_value);
-        symbols[stream * n_sym + pos] = value + cdf_offsets[ci];
+        symbols[stream * n_sym + pos] = value + tb.offsets[ci];
         if (dec.overrun) { st = -2; break; }
     }
     status[stream] = st;
+}
+
+static RansTables make_tables(const uint16_t *ragged, int64_t ragged_len, const int32_t *row_start,
+                              const int32_t *sizes, const int32_t *offsets, int n_cdfs) {
+    RansTables t;
+    t.ragged = ragged; t.row_start = row_start; t.sizes = sizes; t.offsets = offsets;
+    t.n_cdfs = n_cdfs; t.ragged_len = (int)ragged_len;
+    return t;
 }
 
 }  // namespace mmnc
@@ -169,67 +316,108 @@ extern "C" int64_t mmnc_rans_slab_words(int64_t n_sym) {
     return (n_sym * 52 + 31) / 32 + 4 + 16;
 }
 
+extern "C" int mmnc_rans_pack_tables(const int32_t *cdf, const int32_t *cdf_sizes, int n_cdfs, int cdf_stride,
+                                     int32_t *row_start, uint16_t *ragged, int64_t ragged_capacity, void *stream) {
+    MMNC_REQUIRE(n_cdfs > 0 && cdf_stride > 1, "rans_pack_tables: empty CDF table (run update() first)");
+    MMNC_REQUIRE(cdf && cdf_sizes && row_start && ragged, "rans_pack_tables: null pointer");
+    MMNC_REQUIRE(ragged_capacity > 0 && ragged_capacity < (1ll << 30), "rans_pack_tables: bad capacity");
+    rans_pack_tables_kernel<<<1, 256, 0, as_stream(stream)>>>(cdf, cdf_sizes, n_cdfs, cdf_stride, row_start, ragged,
+                                                             (int)ragged_capacity);
+    return after_launch("rans_pack_tables_kernel");
+}
+
 extern "C" int mmnc_rans_encode_batch(const int32_t *symbols, const int32_t *indexes, int64_t channel_period,
-                                      int64_t n_streams, int64_t n_sym, const int32_t *cdf, int n_cdfs,
-                                      int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
-                                      void *staging, uint32_t *slabs, int64_t slab_words, int32_t *nbytes,
-                                      void *stream) {
+                                      int64_t n_streams, int64_t n_sym, const uint16_t *ragged_cdf,
+                                      int64_t ragged_len, const int32_t *row_start, const int32_t *cdf_sizes,
+                                      const int32_t *offsets, int n_cdfs, void *staging, uint32_t *slabs,
+                                      int64_t slab_words, int32_t *nbytes, void *stream) {
     MMNC_REQUIRE(n_streams >= 0 && n_sym >= 0, "rans_encode_batch: negative size");
-    MMNC_REQUIRE(n_cdfs > 0 && cdf_stride > 1, "rans_encode_batch: empty CDF table (run update() first)");
+    MMNC_REQUIRE(n_cdfs > 0 && ragged_len > 0, "rans_encode_batch: empty CDF table (run update() first)");
     MMNC_REQUIRE(indexes != nullptr || channel_period > 0, "rans_encode_batch: need indexes or channel_period");
     MMNC_REQUIRE(slab_words >= mmnc_rans_slab_words(n_sym), "rans_encode_batch: slab_words too small");
     if (n_streams == 0) return MMNC_OK;
-    MMNC_REQUIRE(cdf && cdf_sizes && offsets && slabs && nbytes && (n_sym == 0 || (symbols && staging)),
+    MMNC_REQUIRE(ragged_cdf && row_start && cdf_sizes && offsets && slabs && nbytes && (n_sym == 0 || (symbols && staging)),
                  "rans_encode_batch: null pointer");
+    MMNC_REQUIRE((reinterpret_cast<uintptr_t>(ragged_cdf) & 15) == 0 && (reinterpret_cast<uintptr_t>(staging) & 15) == 0,
+                 "rans_encode_batch: ragged table and staging must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
+    const RansTables tb = make_tables(ragged_cdf, ragged_len, row_start, cdf_sizes, offsets, n_cdfs);
     MMNC_CUDA(cudaMemsetAsync(nbytes, 0, sizeof(int32_t) * (size_t)n_streams, s));
     const int64_t total = n_streams * n_sym;
+    // staging = [uint64 reciprocal x total | uint32 start:range x total]
+    uint64_t *stage_rcp = static_cast<uint64_t *>(staging);
+    uint32_t *stage_sr = reinterpret_cast<uint32_t *>(stage_rcp + total);
     if (total > 0) {
-        int64_t blocks = (total + RANS_MAP_THREADS - 1) / RANS_MAP_THREADS;
-        const int64_t cap = (int64_t)sm_count() * 16;
+        // enough symbols per CTA that copying the table into shared memory pays for itself: each CTA maps at least
+        // as many symbols as the table has entries
+        const size_t table_bytes = ((size_t)ragged_len + 7) / 8 * 16;
+        int64_t blocks = (total + RANS_MAP_THREADS * 8 - 1) / (RANS_MAP_THREADS * 8);
+        const int64_t cap = (int64_t)sm_count() * 4;
         if (blocks > cap) blocks = cap;
-        rans_map_kernel<<<(unsigned)blocks, RANS_MAP_THREADS, 0, s>>>(symbols, indexes, channel_period, n_streams,
-                                                                      n_sym, cdf, n_cdfs, cdf_stride, cdf_sizes,
-                                                                      offsets, static_cast<uint2 *>(staging), nbytes);
+        const bool smem_table = table_bytes <= RANS_SMEM_TABLE_MAX && total >= blocks * ragged_len;
+        if (smem_table) {
+            if (int rc = tmah::ensure_dynamic_smem(rans_map_kernel<true>, table_bytes)) return rc;
+            rans_map_kernel<true><<<(unsigned)blocks, RANS_MAP_THREADS, table_bytes, s>>>(
+                symbols, indexes, channel_period, n_streams, n_sym, tb, stage_sr, stage_rcp, nbytes);
+        } else {
+            blocks = (total + RANS_MAP_THREADS - 1) / RANS_MAP_THREADS;
+            if (blocks > cap * 4) blocks = cap * 4;
+            rans_map_kernel<false><<<(unsigned)blocks, RANS_MAP_THREADS, 0, s>>>(
+                symbols, indexes, channel_period, n_streams, n_sym, tb, stage_sr, stage_rcp, nbytes);
+        }
         if (int rc = after_launch("rans_map_kernel")) return rc;
     }
     rans_encode_kernel<<<(unsigned)((n_streams + RANS_STREAM_THREADS - 1) / RANS_STREAM_THREADS),
-                         RANS_STREAM_THREADS, 0, s>>>(static_cast<const uint2 *>(staging), n_streams, n_sym, slabs,
-                                                      slab_words, nbytes);
+                         RANS_STREAM_THREADS, 0, s>>>(stage_sr, stage_rcp, symbols, indexes, channel_period, n_streams,
+                                                      n_sym, tb, slabs, slab_words, nbytes);
     return after_launch("rans_encode_kernel");
 }
 
 extern "C" int mmnc_rans_compact(const uint32_t *slabs, int64_t slab_words, const int32_t *nbytes,
-                                 int64_t n_streams, int64_t *offsets, uint8_t *packed, int64_t packed_capacity,
+                                 int64_t n_streams, int64_t *meta, uint8_t *packed, int64_t packed_capacity,
                                  void *stream) {
     MMNC_REQUIRE(n_streams >= 0, "rans_compact: negative size");
-    MMNC_REQUIRE(offsets, "rans_compact: null offsets");
+    MMNC_REQUIRE(meta, "rans_compact: null meta");
     cudaStream_t s = as_stream(stream);
     if (n_streams == 0) {
-        MMNC_CUDA(cudaMemsetAsync(offsets, 0, sizeof(int64_t), s));
+        MMNC_CUDA(cudaMemsetAsync(meta, 0, sizeof(int64_t), s));
         return MMNC_OK;
     }
     MMNC_REQUIRE(slabs && nbytes && packed, "rans_compact: null pointer");
-    rans_scan_kernel<<<1, 1024, 0, s>>>(nbytes, n_streams, offsets);
+    rans_scan_kernel<<<1, 1024, 0, s>>>(nbytes, n_streams, meta);
     if (int rc = after_launch("rans_scan_kernel")) return rc;
-    rans_gather_kernel<<<(unsigned)n_streams, 128, 0, s>>>(slabs, slab_words, nbytes, offsets, packed,
-                                                          packed_capacity);
+    rans_gather_kernel<<<(unsigned)((n_streams + 3) / 4), 128, 0, s>>>(slabs, slab_words, nbytes, meta, n_streams, packed,
+                                                                      packed_capacity);
     return after_launch("rans_gather_kernel");
 }
 
-extern "C" int mmnc_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, const int32_t *indexes,
-                                      int64_t channel_period, int64_t n_streams, int64_t n_sym, const int32_t *cdf,
-                                      int n_cdfs, int cdf_stride, const int32_t *cdf_sizes,
-                                      const int32_t *cdf_offsets, int32_t *symbols, int32_t *status, void *stream) {
+extern "C" int mmnc_rans_decode_batch(const uint8_t *packed, const int64_t *offsets, const int32_t *lengths,
+                                      const int32_t *indexes, int64_t channel_period, int64_t n_streams,
+                                      int64_t n_sym, const uint16_t *ragged_cdf, int64_t ragged_len,
+                                      const int32_t *row_start, const int32_t *cdf_sizes, const int32_t *cdf_offsets,
+                                      int n_cdfs, int32_t *symbols, int32_t *status, void *stream) {
     MMNC_REQUIRE(n_streams >= 0 && n_sym >= 0, "rans_decode_batch: negative size");
-    MMNC_REQUIRE(n_cdfs > 0 && cdf_stride > 1, "rans_decode_batch: empty CDF table (run update() first)");
+    MMNC_REQUIRE(n_cdfs > 0 && ragged_len > 0, "rans_decode_batch: empty CDF table (run update() first)");
     MMNC_REQUIRE(indexes != nullptr || channel_period > 0, "rans_decode_batch: need indexes or channel_period");
     if (n_streams == 0) return MMNC_OK;
-    MMNC_REQUIRE(packed && offsets && cdf && cdf_sizes && cdf_offsets && status && (n_sym == 0 || symbols),
+    MMNC_REQUIRE(packed && offsets && lengths && ragged_cdf && row_start && cdf_sizes && cdf_offsets && status &&
+                     (n_sym == 0 || symbols),
                  "rans_decode_batch: null pointer");
-    rans_decode_kernel<<<(unsigned)((n_streams + RANS_STREAM_THREADS - 1) / RANS_STREAM_THREADS),
-                         RANS_STREAM_THREADS, 0, as_stream(stream)>>>(packed, offsets, indexes, channel_period,
-                                                                      n_streams, n_sym, cdf, n_cdfs, cdf_stride,
-                                                                      cdf_sizes, cdf_offsets, symbols, status);
+    MMNC_REQUIRE((reinterpret_cast<uintptr_t>(ragged_cdf) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 3) == 0,
+                 "rans_decode_batch: ragged table must be 16-byte aligned, packed 4-byte aligned");
+    const RansTables tb = make_tables(ragged_cdf, ragged_len, row_start, cdf_sizes, cdf_offsets, n_cdfs);
+    const size_t table_bytes = ((size_t)ragged_len + 7) / 8 * 16;
+    const unsigned blocks = (unsigned)((n_streams + RANS_DECODE_THREADS - 1) / RANS_DECODE_THREADS);
+    // the row search is a chain of dependent loads: from shared memory unless the table is too large for it or the
+    // batch is so small that copying the table costs more than it saves
+    const bool smem_table = table_bytes <= RANS_SMEM_TABLE_MAX && n_sym * 12 >= (int64_t)(table_bytes / 2048);
+    if (smem_table) {
+        if (int rc = tmah::ensure_dynamic_smem(rans_decode_kernel<true>, table_bytes)) return rc;
+        rans_decode_kernel<true><<<blocks, RANS_DECODE_THREADS, table_bytes, as_stream(stream)>>>(
+            packed, offsets, lengths, indexes, channel_period, n_streams, n_sym, tb, symbols, status);
+    } else {
+        rans_decode_kernel<false><<<blocks, RANS_DECODE_THREADS, 0, as_stream(stream)>>>(
+            packed, offsets, lengths, indexes, channel_period, n_streams, n_sym, tb, symbols, status);
+    }
     return after_launch("rans_decode_kernel");
 }

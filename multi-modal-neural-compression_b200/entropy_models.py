@@ -78,6 +78,7 @@ class EntropyModel(nn.Module):
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         # CompressAI resizes these registered buffers on load (update_registered_buffers); same here so that
         # state dicts saved after update() load into a freshly built module.
+        self.__dict__.pop("_rans_tables_cache", None)
         for name in ("_offset", "_quantized_cdf", "_cdf_length", "scale_table"):
             key = prefix + name
             buf = getattr(self, name, None)
@@ -145,6 +146,31 @@ class EntropyModel(nn.Module):
             raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
 
     # ------------------------------------------------------------------ coding (a11, a12)
+    def _rans_tables(self) -> "ops.RansTables":
+        """The ragged 16-bit coding tables the kernels keep in shared memory, rebuilt only when update(), .to() or a
+        state-dict load replaced the CDF buffers."""
+        cdf = self._quantized_cdf
+        key = (cdf.data_ptr(), cdf._version, self._cdf_length.data_ptr(), self._offset.data_ptr())
+        cached = self.__dict__.get("_rans_tables_cache")
+        if cached is None or cached.key != key:
+            cached = ops.RansTables(cdf, self._cdf_length, self._offset)
+            if cached.key != key:  # the buffers were int32 and contiguous already, so no copy was made; keep honest
+                cached.key = key
+            self.__dict__["_rans_tables_cache"] = cached
+        return cached
+
+    def _drop_rans_tables(self):
+        self.__dict__.pop("_rans_tables_cache", None)
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .cpu(): the buffers move, the packed tables do not
+        self._drop_rans_tables()
+        return super()._apply(fn, *args, **kwargs)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_rans_tables_cache", None)  # device scratch is not part of the module's state
+        return state
+
     def compress(self, inputs: Tensor, indexes: Tensor, means: Optional[Tensor] = None) -> List[bytes]:
         if inputs.dim() < 2:
             raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
@@ -154,7 +180,7 @@ class EntropyModel(nn.Module):
         self._check_cdf_length()
         self._check_offsets_size()
         symbols = self.quantize(inputs, "symbols", means)
-        return ops.rans_encode(symbols, indexes, 0, self._quantized_cdf, self._cdf_length, self._offset)
+        return ops.rans_encode(symbols, indexes, 0, self._rans_tables())
 
     def decompress(self, strings, indexes: Tensor, dtype: torch.dtype = torch.float,
                    means: Optional[Tensor] = None) -> Tensor:
@@ -175,7 +201,7 @@ class EntropyModel(nn.Module):
                     if means.size(i) != 1:
                         raise ValueError("Invalid means parameters")
         n_sym = int(indexes[0].numel()) if indexes.size(0) > 0 else 0
-        symbols = ops.rans_decode(strings, indexes, 0, n_sym, self._quantized_cdf, self._cdf_length, self._offset)
+        symbols = ops.rans_decode(strings, indexes, 0, n_sym, self._rans_tables())
         return self.dequantize(symbols.reshape(indexes.size()), means, dtype)
 
 
@@ -291,6 +317,7 @@ class EntropyBottleneck(EntropyModel):
         tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
         self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
         self._cdf_length = pmf_length + 2
+        self._drop_rans_tables()
         return True
 
     # ------------------------------------------------------------------ coding (a11, a12)
@@ -313,7 +340,7 @@ class EntropyBottleneck(EntropyModel):
         # indexes are the channel ids: implicit in the kernel (position // spatial_size), never materialised
         symbols = ops.quantize_symbols(x.detach(), self._get_medians().detach().reshape(1, -1, *([1] * (x.dim() - 2))))
         period = int(x[0, 0].numel())
-        return ops.rans_encode(symbols, None, period, self._quantized_cdf, self._cdf_length, self._offset)
+        return ops.rans_encode(symbols, None, period, self._rans_tables())
 
     def decompress(self, strings, size) -> Tensor:
         if not isinstance(strings, (tuple, list)):
@@ -326,8 +353,7 @@ class EntropyBottleneck(EntropyModel):
         period = 1
         for d in size:
             period *= int(d)
-        symbols = ops.rans_decode(strings, None, period, C * period, self._quantized_cdf, self._cdf_length,
-                                  self._offset)
+        symbols = ops.rans_decode(strings, None, period, C * period, self._rans_tables())
         medians = self._get_medians().detach().reshape(1, -1, *([1] * len(size)))
         return ops.dequantize_symbols(symbols.reshape(output_size), medians)
 
@@ -392,6 +418,7 @@ class GaussianConditional(EntropyModel):
         self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
         self._offset = -pmf_center
         self._cdf_length = pmf_length + 2
+        self._drop_rans_tables()
 
     # ------------------------------------------------------------------ forward (a5)
     def forward(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None,

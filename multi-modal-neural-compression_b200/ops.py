@@ -555,63 +555,174 @@ def build_indexes(scales: Tensor, scale_table: Tensor, scale_bound: float) -> Te
     return out
 
 
-def rans_encode(symbols: Tensor, indexes: Optional[Tensor], channel_period: int, cdf: Tensor, cdf_sizes: Tensor,
-                offsets: Tensor) -> List[bytes]:
-    """symbols (n_streams, ...) int32 on the GPU -> one CompressAI-format byte string per stream."""
-    _need_cuda(symbols, indexes, cdf, cdf_sizes, offsets)
+class RansTables:
+    """Device-side coding tables of one entropy model: CompressAI's `_quantized_cdf` / `_cdf_length` / `_offset`
+    re-packed once (per update()) into the ragged uint16 table the kernels stage in shared memory."""
+
+    def __init__(self, cdf: Tensor, cdf_sizes: Tensor, offsets: Tensor):
+        _need_cuda(cdf, cdf_sizes, offsets)
+        if cdf.dim() != 2 or cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        self.device = cdf.device
+        cdf = cdf.int().contiguous()
+        self.sizes = cdf_sizes.int().contiguous()
+        self.offsets = offsets.int().contiguous()
+        self.n_cdfs = int(cdf.shape[0])
+        self.ragged_len = int(self.sizes.clamp(0, cdf.shape[1]).sum().item())  # once per update(), not per call
+        cap = max(8, (self.ragged_len + 7) // 8 * 8)
+        self.ragged = torch.zeros(cap, dtype=torch.int16, device=self.device)
+        self.row_start = torch.empty(self.n_cdfs + 1, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().mmnc_rans_pack_tables(_p(cdf), _p(self.sizes), self.n_cdfs, int(cdf.shape[1]),
+                                                    _p(self.row_start), _p(self.ragged), cap, _stream()))
+        self.key = (cdf.data_ptr(), cdf._version, self.sizes.data_ptr(), self.offsets.data_ptr())
+
+
+class _RansWorkspace:
+    """Grow-only device scratch + pinned host staging, one per device: `compress` / `decompress` allocate nothing in
+    steady state and move their results with one metadata copy and one payload copy."""
+
+    _per_device = {}
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    @classmethod
+    def get(cls, device) -> "_RansWorkspace":
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        ws = cls._per_device.get(key)
+        if ws is None:
+            ws = cls._per_device[key] = cls(device)
+        return ws
+
+    def dev(self, name: str, nbytes: int) -> Tensor:
+        t = self.bufs.get(name)
+        if t is None or t.numel() < nbytes:
+            t = self.bufs[name] = torch.empty(max(256, int(nbytes * 1.25)), dtype=torch.uint8, device=self.device)
+        return t
+
+    def host(self, name: str, nbytes: int) -> Tensor:
+        t = self.bufs.get(name)
+        if t is None or t.numel() < nbytes:
+            t = self.bufs[name] = torch.empty(max(4096, int(nbytes * 1.25)), dtype=torch.uint8, pin_memory=True)
+        return t
+
+
+def rans_encode_device(symbols: Tensor, indexes: Optional[Tensor], channel_period: int, tables: RansTables):
+    """The device part of `rans_encode`: -> (meta, packed, n_streams) still on the GPU, nothing synchronised.
+    meta = int64 offsets[n + 1] | int32 nbytes[n]; packed = the strings back to back."""
+    _need_cuda(symbols, indexes)
     n_streams = symbols.shape[0]
-    sym = symbols.reshape(n_streams, -1).contiguous()
+    sym = symbols.reshape(n_streams, -1)
+    if sym.dtype != torch.int32 or not sym.is_contiguous():
+        sym = sym.int().contiguous()
     n_sym = sym.shape[1]
     if indexes is not None:
-        indexes = indexes.reshape(n_streams, -1).int().contiguous()
-    dev = sym.device
+        indexes = indexes.reshape(n_streams, -1)
+        if indexes.dtype != torch.int32 or not indexes.is_contiguous():
+            indexes = indexes.int().contiguous()
     L = _lib.lib()
+    ws = _RansWorkspace.get(sym.device)
     slab_words = int(L.mmnc_rans_slab_words(n_sym))
-    staging = torch.empty(max(1, n_streams * n_sym * 2), dtype=torch.int32, device=dev)
-    slabs = torch.empty((max(1, n_streams), slab_words), dtype=torch.int32, device=dev)
-    nbytes = torch.empty(max(1, n_streams), dtype=torch.int32, device=dev)
-    offs = torch.empty(n_streams + 1, dtype=torch.int64, device=dev)
-    packed = torch.empty(max(1, n_streams) * slab_words * 4, dtype=torch.uint8, device=dev)
-    cdf, cdf_sizes, offsets = cdf.int().contiguous(), cdf_sizes.int().contiguous(), offsets.int().contiguous()
-    _lib.check(L.mmnc_rans_encode_batch(_p(sym), _p(indexes), int(channel_period), n_streams, n_sym, _p(cdf),
-                                        cdf.shape[0], cdf.shape[1], _p(cdf_sizes), _p(offsets), _p(staging), _p(slabs),
-                                        slab_words, _p(nbytes), _stream()))
-    _lib.check(L.mmnc_rans_compact(_p(slabs), slab_words, _p(nbytes), n_streams, _p(offs), _p(packed), packed.numel(),
+    n1 = max(1, n_streams)
+    staging = ws.dev("staging", n1 * max(1, n_sym) * 12)
+    slabs = ws.dev("slabs", n1 * slab_words * 4)
+    nbytes = ws.dev("nbytes", n1 * 4)
+    meta = ws.dev("meta", (n1 + 1) * 8 + n1 * 4)
+    packed = ws.dev("packed", n1 * slab_words * 4)
+    _lib.check(L.mmnc_rans_encode_batch(_p(sym), _p(indexes), int(channel_period), n_streams, n_sym, _p(tables.ragged),
+                                        tables.ragged_len, _p(tables.row_start), _p(tables.sizes), _p(tables.offsets),
+                                        tables.n_cdfs, _p(staging), _p(slabs), slab_words, _p(nbytes), _stream()))
+    _lib.check(L.mmnc_rans_compact(_p(slabs), slab_words, _p(nbytes), n_streams, _p(meta), _p(packed), packed.numel(),
                                    _stream()))
-    meta = torch.cat([offs, nbytes[:n_streams].long()]).cpu()  # one sync D2H for offsets + per-stream status
-    offs_h, nb_h = meta[: n_streams + 1].tolist(), meta[n_streams + 1:].tolist()
-    if any(v < 0 for v in nb_h):
-        bad = [i for i, v in enumerate(nb_h) if v < 0]
-        raise ValueError(f"rans_encode: malformed input for streams {bad[:8]} (index out of range or zero-width CDF bin)")
-    blob = packed[: offs_h[-1]].cpu().numpy().tobytes()
-    return [blob[offs_h[i]: offs_h[i + 1]] for i in range(n_streams)]
+    return meta, packed, n_streams
 
 
-def rans_decode(strings: Sequence[bytes], indexes: Optional[Tensor], channel_period: int, n_sym: int, cdf: Tensor,
-                cdf_sizes: Tensor, offsets: Tensor) -> Tensor:
-    """byte strings -> (n_streams, n_sym) int32 symbols on the GPU."""
-    _need_cuda(indexes, cdf, cdf_sizes, offsets)
-    n_streams = len(strings)
-    dev = cdf.device
-    lens = [len(s) for s in strings]
-    offs_h = [0]
-    for n in lens:
-        offs_h.append(offs_h[-1] + n)
-    blob = b"".join(strings)
-    packed = torch.frombuffer(bytearray(blob) if blob else bytearray(4), dtype=torch.uint8).to(dev, non_blocking=False)
-    offs = torch.tensor(offs_h, dtype=torch.int64).to(dev)
+def rans_encode(symbols: Tensor, indexes: Optional[Tensor], channel_period: int, tables: RansTables) -> List[bytes]:
+    """symbols (n_streams, ...) int32 on the GPU -> one CompressAI-format byte string per stream."""
+    meta, packed, n = rans_encode_device(symbols, indexes, channel_period, tables)
+    if n == 0:
+        return []
+    ws = _RansWorkspace.get(symbols.device)
+    meta_bytes = (n + 1) * 8 + n * 4
+    stream = torch.cuda.current_stream(symbols.device)
+    host_meta = ws.host("host_meta", meta_bytes)
+    host_meta[:meta_bytes].copy_(meta[:meta_bytes], non_blocking=True)  # D2H 1: offsets + per-stream status
+    stream.synchronize()
+    hm = host_meta.numpy()
+    offs_h = hm[: (n + 1) * 8].view("int64")
+    nb_h = hm[(n + 1) * 8: meta_bytes].view("int32")
+    if (nb_h < 0).any():
+        bad = [int(i) for i in (nb_h < 0).nonzero()[0][:8]]
+        raise ValueError(f"rans_encode: malformed input for streams {bad} (index out of range or zero-width CDF bin)")
+    total = int(offs_h[n])
+    host_blob = ws.host("host_blob", total)
+    host_blob[:total].copy_(packed[:total], non_blocking=True)          # D2H 2: exactly the coded bytes
+    stream.synchronize()
+    blob = host_blob.numpy()[:total].tobytes()
+    cuts = offs_h.tolist()
+    return [blob[cuts[i]: cuts[i + 1]] for i in range(n)]
+
+
+def rans_decode_device(blob_dev: Tensor, offs_dev: Tensor, lens_dev: Tensor, n_streams: int,
+                       indexes: Optional[Tensor], channel_period: int, n_sym: int, tables: RansTables):
+    """The device part of `rans_decode`: -> (symbols (n_streams, n_sym) int32, status (n_streams,) int32)."""
+    dev = blob_dev.device
     if indexes is not None:
-        indexes = indexes.reshape(n_streams, -1).int().contiguous()
+        indexes = indexes.reshape(n_streams, -1)
+        if indexes.dtype != torch.int32 or not indexes.is_contiguous():
+            indexes = indexes.int().contiguous()
         if indexes.shape[1] != n_sym:
             raise ValueError("indexes do not match the number of symbols")
     out = torch.empty((n_streams, n_sym), dtype=torch.int32, device=dev)
     status = torch.zeros(max(1, n_streams), dtype=torch.int32, device=dev)
-    cdf, cdf_sizes, offsets = cdf.int().contiguous(), cdf_sizes.int().contiguous(), offsets.int().contiguous()
-    _lib.check(_lib.lib().mmnc_rans_decode_batch(_p(packed), _p(offs), _p(indexes), int(channel_period), n_streams,
-                                                 n_sym, _p(cdf), cdf.shape[0], cdf.shape[1], _p(cdf_sizes), _p(offsets),
-                                                 _p(out), _p(status), _stream()))
-    st = status[:n_streams].cpu().tolist()
-    if any(v != 0 for v in st):
-        bad = [(i, v) for i, v in enumerate(st) if v != 0]
-        raise ValueError(f"rans_decode: corrupt or truncated stream(s) {bad[:8]}")
+    _lib.check(_lib.lib().mmnc_rans_decode_batch(_p(blob_dev), _p(offs_dev), _p(lens_dev), _p(indexes),
+                                                 int(channel_period), n_streams, n_sym, _p(tables.ragged),
+                                                 tables.ragged_len, _p(tables.row_start), _p(tables.sizes),
+                                                 _p(tables.offsets), tables.n_cdfs, _p(out), _p(status), _stream()))
+    return out, status
+
+
+def rans_upload(strings: Sequence[bytes], device):
+    """byte strings -> (blob, offsets int64, lengths int32) on the device with ONE pinned host-to-device copy.  Every
+    stream starts at a multiple of 4 bytes (the kernel reads whole words)."""
+    import numpy as np
+
+    n = len(strings)
+    lens = np.fromiter((len(s) for s in strings), dtype=np.int64, count=n)
+    padded = (lens + 3) & ~3
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(padded, out=offs[1:])
+    total = int(offs[n])
+    head = (n + 1) * 8 + ((n * 4 + 7) // 8) * 8
+    ws = _RansWorkspace.get(device)
+    host = ws.host("host_up", head + max(total, 4))
+    hv = host.numpy()
+    hv[: (n + 1) * 8].view("int64")[:] = offs
+    hv[(n + 1) * 8: (n + 1) * 8 + n * 4].view("int32")[:] = lens.astype(np.int32)
+    if (padded == lens).all():
+        hv[head: head + total] = np.frombuffer(b"".join(strings), dtype=np.uint8) if total else 0
+    else:  # malformed lengths: place each stream at its aligned offset
+        for i, s_ in enumerate(strings):
+            hv[head + offs[i]: head + offs[i] + len(s_)] = np.frombuffer(s_, dtype=np.uint8)
+    dev_buf = ws.dev("dev_up", head + max(total, 4))
+    dev_buf[: head + max(total, 4)].copy_(host[: head + max(total, 4)], non_blocking=True)
+    offs_dev = dev_buf[: (n + 1) * 8].view(torch.int64)
+    lens_dev = dev_buf[(n + 1) * 8: (n + 1) * 8 + n * 4].view(torch.int32) if n else dev_buf[:0].view(torch.int32)
+    return dev_buf[head:], offs_dev, lens_dev
+
+
+def rans_decode(strings: Sequence[bytes], indexes: Optional[Tensor], channel_period: int, n_sym: int,
+                tables: RansTables) -> Tensor:
+    """byte strings -> (n_streams, n_sym) int32 symbols on the GPU."""
+    _need_cuda(indexes)
+    n_streams = len(strings)
+    dev = tables.device
+    blob_dev, offs_dev, lens_dev = rans_upload(strings, dev)
+    out, status = rans_decode_device(blob_dev, offs_dev, lens_dev, n_streams, indexes, channel_period, n_sym, tables)
+    if n_streams:
+        st = status[:n_streams].cpu()  # also the point where the pinned upload buffer may be reused
+        if bool((st != 0).any()):
+            bad = [(int(i), int(st[i])) for i in (st != 0).nonzero().reshape(-1)[:8]]
+            raise ValueError(f"rans_decode: corrupt or truncated stream(s) {bad}")
     return out

@@ -35,7 +35,9 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"spatial" in lib.mmnc_last_error()
     rc = lib.mmnc_eb_forward(None, 1, 1, 1, None, None, 9, None, 0, 0, 1e-9, 0, None, None, None, None)
     assert rc == -1
-    assert lib.mmnc_rans_encode_batch(None, None, 0, 1, 1, None, 0, 0, None, None, None, None, 100, None, None) == -1
+    assert lib.mmnc_rans_encode_batch(None, None, 0, 1, 1, None, 0, None, None, None, 0, None, None, 100, None, None) == -1
+    assert lib.mmnc_rans_decode_batch(None, None, None, None, 0, 1, 1, None, 0, None, None, None, 0, None, None, None) == -1
+    assert lib.mmnc_rans_pack_tables(None, None, 0, 0, None, None, 0, None) == -1
     # empty inputs are fine and launch nothing
     before = mm.launch_count()
     assert lib.mmnc_eb_forward(None, 0, 4, 1, None, None, 0, None, 0, 0, 1e-9, 0, None, None, None, None) == 0

@@ -564,10 +564,9 @@ def test_rans_golden_streams(gc_pair):
     fx = load_golden()
     for sym, idx, want in zip(fx["rans_sym"], fx["rans_idx"], fx["rans_bytes"]):
         s = mm.ops.rans_encode(torch.from_numpy(sym).to(DEV).reshape(1, -1), torch.from_numpy(idx).to(DEV).reshape(1, -1),
-                               0, ours._quantized_cdf, ours._cdf_length, ours._offset)
+                               0, ours._rans_tables())
         assert s == [want.tobytes()]
-        back = mm.ops.rans_decode(s, torch.from_numpy(idx).to(DEV).reshape(1, -1), 0, sym.size, ours._quantized_cdf,
-                                  ours._cdf_length, ours._offset)
+        back = mm.ops.rans_decode(s, torch.from_numpy(idx).to(DEV).reshape(1, -1), 0, sym.size, ours._rans_tables())
         assert np.array_equal(back.cpu().numpy().reshape(-1), sym)
 
 
