@@ -101,7 +101,10 @@ class MultiTaskCompressor(nn.Module):
         # per-instance switch (default from MMNC_SERIAL_HEADS at construction time); see _run_heads
         self.concurrent_heads = os.environ.get("MMNC_SERIAL_HEADS", "0") != "1"
         self._optimizers = None
-        self.grad_sync = None  # set by parallel.DataParallel: called between backward() and optimizer.step()
+        # set by parallel.DataParallel: grad_zero() replaces optimizer.zero_grad (one memset of the flat gradient
+        # bucket), grad_sync() is called between backward() and optimizer.step()
+        self.grad_sync = None
+        self.grad_zero = None
 
     def get_model_name(self):
         return self.__class__.__name__
@@ -322,14 +325,17 @@ class MultiTaskCompressor(nn.Module):
         loss, log_dict = self.rate_distortion_loss(batch, x_hats, likelihoods, log_dir)
         if is_train:
             main_opt, aux_opt = self.optimizers()
-            main_opt.zero_grad(set_to_none=False)
+            if self.grad_zero is not None:
+                self.grad_zero()
+            else:
+                main_opt.zero_grad(set_to_none=True)  # backward then assigns the gradients: no zeroing, no adds
             loss.backward()
             if self.grad_sync is not None:
                 self.grad_sync()
             main_opt.step()
             aux_loss = self.auxiliary_loss()
             log_dict[f"{log_dir}/aux_loss"] = aux_loss.detach()
-            aux_opt.zero_grad(set_to_none=False)
+            aux_opt.zero_grad(set_to_none=True)
             aux_loss.backward()
             aux_opt.step()
             self.lr_schedulers().step()

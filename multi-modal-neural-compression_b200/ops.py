@@ -586,6 +586,7 @@ class _RansWorkspace:
     def __init__(self, device):
         self.device = device
         self.bufs = {}
+        self.upload_done = None  # CUDA event: the last asynchronous copy out of the pinned upload buffer
 
     @classmethod
     def get(cls, device) -> "_RansWorkspace":
@@ -696,6 +697,8 @@ def rans_upload(strings: Sequence[bytes], device):
     total = int(offs[n])
     head = (n + 1) * 8 + ((n * 4 + 7) // 8) * 8
     ws = _RansWorkspace.get(device)
+    if ws.upload_done is not None:
+        ws.upload_done.synchronize()  # the previous upload may still be reading the pinned buffer
     host = ws.host("host_up", head + max(total, 4))
     hv = host.numpy()
     hv[: (n + 1) * 8].view("int64")[:] = offs
@@ -707,6 +710,8 @@ def rans_upload(strings: Sequence[bytes], device):
             hv[head + offs[i]: head + offs[i] + len(s_)] = np.frombuffer(s_, dtype=np.uint8)
     dev_buf = ws.dev("dev_up", head + max(total, 4))
     dev_buf[: head + max(total, 4)].copy_(host[: head + max(total, 4)], non_blocking=True)
+    ws.upload_done = torch.cuda.Event()
+    ws.upload_done.record(torch.cuda.current_stream(dev_buf.device))
     offs_dev = dev_buf[: (n + 1) * 8].view(torch.int64)
     lens_dev = dev_buf[(n + 1) * 8: (n + 1) * 8 + n * 4].view(torch.int32) if n else dev_buf[:0].view(torch.int32)
     return dev_buf[head:], offs_dev, lens_dev

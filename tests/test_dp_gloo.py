@@ -42,13 +42,17 @@ def _worker(rank, world, port, out):
 
     torch.manual_seed(100 + rank)  # different init per rank: broadcast must fix it
     toy = _Toy()
-    dp = mm.DataParallel(toy)
+    dp = mm.DataParallel(toy, n_buckets=3)   # [log_vars, bias | weight]: every all-reduce starts from a grad hook
+    assert len(dp.bucket.slices) == 2 and dp.bucket.counts == [2, 1]
     torch.manual_seed(7)
-    x_all = torch.randn(8, 6)
-    shard = x_all[rank * 4:(rank + 1) * 4]
-    toy.loss(shard).backward()
-    assert dp.bucket.check_views()
-    toy.grad_sync()
+    x_warm, x_all = torch.randn(8, 6), torch.randn(8, 6)
+    for x in (x_warm, x_all):                # two steps: the arrival state must re-arm, the bucket must be re-zeroed
+        toy.grad_zero()
+        toy.loss(x[rank * 4:(rank + 1) * 4]).backward()
+        assert dp.bucket.check_views()
+        assert all(dp._launched), "every bucket's all-reduce should have been issued during backward"
+        toy.grad_sync()
+        assert not any(dp._launched) and not dp._work
     res = {"grad": dp.bucket.flat.clone(), "w": toy.model["net"].weight.detach().clone(),
            "offset": mm.ops.noise_source.next(10)[1]}
     if rank == 0:
@@ -86,3 +90,11 @@ def test_flat_bucket_single_process():
     for p in toy.get_main_parameters():
         p.grad.zero_()
     assert b.flat.abs().sum() == 0
+    # several buckets: contiguous, cover the buffer, every parameter in exactly one
+    b3 = mm.FlatGradBucket(toy.get_main_parameters() + [toy.loss_balancer.log_vars], n_buckets=2)
+    assert b3.bounds[0][0] == 0 and b3.bounds[-1][1] == b3.flat.numel()
+    assert all(b3.bounds[i][1] == b3.bounds[i + 1][0] for i in range(len(b3.bounds) - 1))
+    assert sum(b3.counts) == 3 and sorted(set(b3.bucket_of.values())) == list(range(len(b3.bounds)))
+    toy.loss(torch.randn(4, 6)).backward()
+    b3.zero()
+    assert b3.flat.abs().sum() == 0 and b3.check_views()
