@@ -188,7 +188,7 @@ def test_oracle_likelihood_formulas_against_scipy_float64():
     s = np.maximum(scales, 0.11)
     v = np.abs(np.round(y))
     want = np.maximum(scipy.stats.norm.cdf((0.5 - v) / s) - scipy.stats.norm.cdf((-0.5 - v) / s), 1e-9)
-    got = lik.reshape(-1).numpy()
+    got = lik.detach().reshape(-1).numpy()
     big = want > 1e-7
     assert np.max(np.abs(got - want)[big] / want[big]) < 1e-9
     # entropy bottleneck: the MLP in numpy float64 + expit
@@ -213,7 +213,7 @@ def test_oracle_likelihood_formulas_against_scipy_float64():
 
     lo, up = logits(zq - 0.5), logits(zq + 0.5)
     want = np.maximum(np.abs(scipy.special.expit(up) - scipy.special.expit(lo)), 1e-9)
-    got = lik.numpy()
+    got = lik.detach().numpy()
     big = want > 1e-7
     assert np.max(np.abs(got - want)[big] / want[big]) < 1e-9
 
@@ -224,7 +224,7 @@ def rans_encode_py(symbols, indexes, cdfs, cdf_sizes, offsets):
     L, prec, bbits = 1 << 31, 16, 4
     syms = []  # (start, range, bypass)
     for s, ci in zip(symbols, indexes):
-        cdf, max_value = cdfs[ci], cdf_sizes[ci] - 2
+        cdf, max_value = cdfs[ci], int(cdf_sizes[ci]) - 2
         value, raw = int(s) - int(offsets[ci]), 0
         if value < 0:
             raw, value = -2 * value - 1, max_value
