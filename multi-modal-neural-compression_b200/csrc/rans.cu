@@ -26,6 +26,7 @@ namespace mmnc {
 constexpr int RANS_MAP_THREADS = 256;
 constexpr int RANS_STREAM_THREADS = 32;
 constexpr int RANS_DECODE_THREADS = 128;
+constexpr int RANS_CHUNK = 8;  // independent loads kept in flight per thread in the sequential passes
 constexpr size_t RANS_SMEM_TABLE_MAX = 200 * 1024;
 
 struct RansTables {
@@ -72,7 +73,7 @@ template <bool kSmemTable>
 __global__ void __launch_bounds__(RANS_MAP_THREADS)
 rans_map_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t channel_period,
                 int64_t n_streams, int64_t n_sym, const RansTables tb, uint32_t *__restrict__ stage_sr,
-                uint64_t *__restrict__ stage_rcp, int32_t *__restrict__ nbytes) {
+                uint64_t *__restrict__ stage_rcp) {
     extern __shared__ __align__(16) uint8_t rans_smem[];
     const uint16_t *table = tb.ragged;
     if (kSmemTable) {
@@ -92,9 +93,7 @@ rans_map_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__
         const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
         uint32_t sr = 0u;
         uint64_t rcp = 0ull;
-        if (ci < 0 || ci >= tb.n_cdfs) {
-            nbytes[stream] = -1;  // malformed index: flag the stream (pass 2 keeps the flag)
-        } else {
+        if (ci >= 0 && ci < tb.n_cdfs) {  // a malformed index leaves range = 0: pass 2 flags the stream
             const int32_t max_value = tb.sizes[ci] - 2;
             uint32_t raw;
             const int slot = rans_map_symbol(symbols[stream * n_sym + pos], tb.offsets[ci], max_value, &raw);
@@ -119,30 +118,36 @@ rans_encode_kernel(const uint32_t *__restrict__ stage_sr, const uint64_t *__rest
                    int64_t slab_words, int32_t *__restrict__ nbytes) {
     const int64_t stream = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (stream >= n_streams) return;
-    if (nbytes[stream] < 0) return;
     uint32_t *slab = slabs + stream * slab_words;
     RansEnc enc;
     enc.init(slab + slab_words);
     bool ok = true;
-    // the staging reads do not depend on the coder state: keep the next entries in flight while the state chain runs
-    int64_t pos = n_sym - 1;
-    uint32_t sr_n = 0u;
-    uint64_t rcp_n = 0ull;
-    if (pos >= 0) { sr_n = stage_sr[pos * n_streams + stream]; rcp_n = stage_rcp[pos * n_streams + stream]; }
-    for (; pos >= 0; --pos) {
-        const uint32_t sr = sr_n;
-        const uint64_t rcp = rcp_n;
-        if (pos > 0) { sr_n = stage_sr[(pos - 1) * n_streams + stream]; rcp_n = stage_rcp[(pos - 1) * n_streams + stream]; }
-        const uint32_t start = sr & 0xFFFFu, range = sr >> 16;
-        if (range == 0u || enc.ptr - slab < 16) { ok = false; break; }
-        if (start + range == 65536u) {
-            // the escape slot is the last one of its row; its payload is re-derived from the symbol (rare path)
-            const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
-            uint32_t raw;
-            rans_map_symbol(symbols[stream * n_sym + pos], tb.offsets[ci], tb.sizes[ci] - 2, &raw);
-            rans_put_escape_reversed(enc, raw);
+    // The staging reads do not depend on the coder state: RANS_CHUNK entries are fetched together (one L2 round trip
+    // per chunk instead of one per symbol), then the state chain runs over them.
+    for (int64_t hi = n_sym; hi > 0 && ok; hi -= RANS_CHUNK) {
+        uint32_t sr_c[RANS_CHUNK];
+        uint64_t rcp_c[RANS_CHUNK];
+#pragma unroll
+        for (int k = 0; k < RANS_CHUNK; ++k) {
+            const int64_t pos = hi - 1 - k;
+            sr_c[k] = pos >= 0 ? stage_sr[pos * n_streams + stream] : 0u;
+            rcp_c[k] = pos >= 0 ? stage_rcp[pos * n_streams + stream] : 0ull;
         }
-        enc.put_rcp(start, range, rcp);
+#pragma unroll
+        for (int k = 0; k < RANS_CHUNK; ++k) {
+            const int64_t pos = hi - 1 - k;
+            if (pos < 0) break;
+            const uint32_t start = sr_c[k] & 0xFFFFu, range = sr_c[k] >> 16;
+            if (range == 0u || enc.ptr - slab < 16) { ok = false; break; }
+            if (start + range == 65536u) {
+                // the escape slot is the last one of its row; its payload is re-derived from the symbol (rare path)
+                const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
+                uint32_t raw;
+                rans_map_symbol(symbols[stream * n_sym + pos], tb.offsets[ci], tb.sizes[ci] - 2, &raw);
+                rans_put_escape_reversed(enc, raw);
+            }
+            enc.put_rcp(start, range, rcp_c[k]);
+        }
     }
     if (!ok) { nbytes[stream] = -2; return; }
     enc.flush();
@@ -263,13 +268,22 @@ rans_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restrict
                    int32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t rans_smem[];
     const uint16_t *table = tb.ragged;
+    const int32_t *row_start = tb.row_start, *sizes = tb.sizes, *offs = tb.offsets;
     if (kSmemTable) {
+        // [ragged table | row_start | sizes | offsets]: every lookup of the symbol loop is a shared-memory read
         const uint4 *src = reinterpret_cast<const uint4 *>(tb.ragged);
         uint4 *dst = reinterpret_cast<uint4 *>(rans_smem);
         const int nvec = (tb.ragged_len + 7) >> 3;
         for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+        int32_t *small = reinterpret_cast<int32_t *>(rans_smem + (size_t)nvec * 16);
+        for (int i = threadIdx.x; i < tb.n_cdfs; i += blockDim.x) {
+            small[i] = tb.row_start[i];
+            small[tb.n_cdfs + i] = tb.sizes[i];
+            small[2 * tb.n_cdfs + i] = tb.offsets[i];
+        }
         __syncthreads();
         table = reinterpret_cast<const uint16_t *>(rans_smem);
+        row_start = small; sizes = small + tb.n_cdfs; offs = small + 2 * tb.n_cdfs;
     }
     const int64_t stream = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (stream >= n_streams) return;
@@ -279,21 +293,31 @@ rans_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restrict
     if (len_bytes < 8 || (len_bytes & 3)) { status[stream] = -1; return; }
     RansDecW dec;
     dec.init(reinterpret_cast<const uint32_t *>(packed + b0), reinterpret_cast<const uint32_t *>(packed + b0 + len_bytes));
-    for (int64_t pos = 0; pos < n_sym; ++pos) {
-        const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
-        if (ci < 0 || ci >= tb.n_cdfs) { st = -3; break; }
-        const int32_t len = tb.sizes[ci];
-        const int32_t max_value = len - 2;
-        if (max_value < 0) { st = -4; break; }
-        const uint16_t *row = table + tb.row_start[ci];
-        const int slot = rans_find_slot_u16(row, len, dec.peek());
-        if (slot < 0 || slot > max_value) { st = -4; break; }
-        const uint32_t start = row[slot];
-        dec.advance(start, ((uint32_t)row[slot + 1] - start) & 0xFFFFu);
-        int32_t value = slot;
-        if (slot == max_value) value = dec.get_escape(max_value);
-        symbols[stream * n_sym + pos] = value + tb.offsets[ci];
-        if (dec.overrun) { st = -2; break; }
+    for (int64_t p0 = 0; p0 < n_sym && st == 0; p0 += RANS_CHUNK) {
+        // the CDF indexes do not depend on the decoder state: fetch a chunk, then run the state chain over it
+        int32_t ci_c[RANS_CHUNK];
+#pragma unroll
+        for (int k = 0; k < RANS_CHUNK; ++k)
+            ci_c[k] = (p0 + k < n_sym) ? stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, p0 + k) : 0;
+#pragma unroll
+        for (int k = 0; k < RANS_CHUNK; ++k) {
+            const int64_t pos = p0 + k;
+            if (pos >= n_sym) break;
+            const int32_t ci = ci_c[k];
+            if (ci < 0 || ci >= tb.n_cdfs) { st = -3; break; }
+            const int32_t len = sizes[ci];
+            const int32_t max_value = len - 2;
+            if (max_value < 0) { st = -4; break; }
+            const uint16_t *row = table + row_start[ci];
+            const int slot = rans_find_slot_u16(row, len, dec.peek());
+            if (slot < 0 || slot > max_value) { st = -4; break; }
+            const uint32_t start = row[slot];
+            dec.advance(start, ((uint32_t)row[slot + 1] - start) & 0xFFFFu);
+            int32_t value = slot;
+            if (slot == max_value) value = dec.get_escape(max_value);
+            symbols[stream * n_sym + pos] = value + offs[ci];
+            if (dec.overrun) { st = -2; break; }
+        }
     }
     status[stream] = st;
 }
@@ -342,7 +366,6 @@ extern "C" int mmnc_rans_encode_batch(const int32_t *symbols, const int32_t *ind
                  "rans_encode_batch: ragged table and staging must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
     const RansTables tb = make_tables(ragged_cdf, ragged_len, row_start, cdf_sizes, offsets, n_cdfs);
-    MMNC_CUDA(cudaMemsetAsync(nbytes, 0, sizeof(int32_t) * (size_t)n_streams, s));
     const int64_t total = n_streams * n_sym;
     // staging = [uint64 reciprocal x total | uint32 start:range x total]
     uint64_t *stage_rcp = static_cast<uint64_t *>(staging);
@@ -358,12 +381,12 @@ extern "C" int mmnc_rans_encode_batch(const int32_t *symbols, const int32_t *ind
         if (smem_table) {
             if (int rc = tmah::ensure_dynamic_smem(rans_map_kernel<true>, table_bytes)) return rc;
             rans_map_kernel<true><<<(unsigned)blocks, RANS_MAP_THREADS, table_bytes, s>>>(
-                symbols, indexes, channel_period, n_streams, n_sym, tb, stage_sr, stage_rcp, nbytes);
+                symbols, indexes, channel_period, n_streams, n_sym, tb, stage_sr, stage_rcp);
         } else {
             blocks = (total + RANS_MAP_THREADS - 1) / RANS_MAP_THREADS;
             if (blocks > cap * 4) blocks = cap * 4;
             rans_map_kernel<false><<<(unsigned)blocks, RANS_MAP_THREADS, 0, s>>>(
-                symbols, indexes, channel_period, n_streams, n_sym, tb, stage_sr, stage_rcp, nbytes);
+                symbols, indexes, channel_period, n_streams, n_sym, tb, stage_sr, stage_rcp);
         }
         if (int rc = after_launch("rans_map_kernel")) return rc;
     }
@@ -406,7 +429,7 @@ extern "C" int mmnc_rans_decode_batch(const uint8_t *packed, const int64_t *offs
     MMNC_REQUIRE((reinterpret_cast<uintptr_t>(ragged_cdf) & 15) == 0 && (reinterpret_cast<uintptr_t>(packed) & 3) == 0,
                  "rans_decode_batch: ragged table must be 16-byte aligned, packed 4-byte aligned");
     const RansTables tb = make_tables(ragged_cdf, ragged_len, row_start, cdf_sizes, cdf_offsets, n_cdfs);
-    const size_t table_bytes = ((size_t)ragged_len + 7) / 8 * 16;
+    const size_t table_bytes = ((size_t)ragged_len + 7) / 8 * 16 + (size_t)n_cdfs * 12;
     const unsigned blocks = (unsigned)((n_streams + RANS_DECODE_THREADS - 1) / RANS_DECODE_THREADS);
     // the row search is a chain of dependent loads: from shared memory unless the table is too large for it or the
     // batch is so small that copying the table costs more than it saves

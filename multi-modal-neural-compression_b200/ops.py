@@ -587,6 +587,7 @@ class _RansWorkspace:
         self.device = device
         self.bufs = {}
         self.upload_done = None  # CUDA event: the last asynchronous copy out of the pinned upload buffer
+        self.bytes_per_stream = {}  # symbols per stream -> running estimate that sizes rans_encode's single D2H copy
 
     @classmethod
     def get(cls, device) -> "_RansWorkspace":
@@ -610,8 +611,9 @@ class _RansWorkspace:
 
 
 def rans_encode_device(symbols: Tensor, indexes: Optional[Tensor], channel_period: int, tables: RansTables):
-    """The device part of `rans_encode`: -> (meta, packed, n_streams) still on the GPU, nothing synchronised.
-    meta = int64 offsets[n + 1] | int32 nbytes[n]; packed = the strings back to back."""
+    """The device part of `rans_encode`: -> (out, meta_bytes_aligned, n_streams) still on the GPU, nothing
+    synchronised.  out = [meta | packed]: meta = int64 offsets[n + 1] | int32 nbytes[n] (padded to 16 bytes), packed =
+    the strings back to back."""
     _need_cuda(symbols, indexes)
     n_streams = symbols.shape[0]
     sym = symbols.reshape(n_streams, -1)
@@ -629,38 +631,46 @@ def rans_encode_device(symbols: Tensor, indexes: Optional[Tensor], channel_perio
     staging = ws.dev("staging", n1 * max(1, n_sym) * 12)
     slabs = ws.dev("slabs", n1 * slab_words * 4)
     nbytes = ws.dev("nbytes", n1 * 4)
-    meta = ws.dev("meta", (n1 + 1) * 8 + n1 * 4)
-    packed = ws.dev("packed", n1 * slab_words * 4)
+    meta_al = ((n1 + 1) * 8 + n1 * 4 + 15) // 16 * 16
+    cap = n1 * slab_words * 4
+    out = ws.dev("out", meta_al + cap)
     _lib.check(L.mmnc_rans_encode_batch(_p(sym), _p(indexes), int(channel_period), n_streams, n_sym, _p(tables.ragged),
                                         tables.ragged_len, _p(tables.row_start), _p(tables.sizes), _p(tables.offsets),
                                         tables.n_cdfs, _p(staging), _p(slabs), slab_words, _p(nbytes), _stream()))
-    _lib.check(L.mmnc_rans_compact(_p(slabs), slab_words, _p(nbytes), n_streams, _p(meta), _p(packed), packed.numel(),
+    _lib.check(L.mmnc_rans_compact(_p(slabs), slab_words, _p(nbytes), n_streams, _p(out), _p(out[meta_al:]), cap,
                                    _stream()))
-    return meta, packed, n_streams
+    return out, meta_al, n_streams
 
 
 def rans_encode(symbols: Tensor, indexes: Optional[Tensor], channel_period: int, tables: RansTables) -> List[bytes]:
     """symbols (n_streams, ...) int32 on the GPU -> one CompressAI-format byte string per stream."""
-    meta, packed, n = rans_encode_device(symbols, indexes, channel_period, tables)
+    out, meta_al, n = rans_encode_device(symbols, indexes, channel_period, tables)
     if n == 0:
         return []
     ws = _RansWorkspace.get(symbols.device)
-    meta_bytes = (n + 1) * 8 + n * 4
     stream = torch.cuda.current_stream(symbols.device)
-    host_meta = ws.host("host_meta", meta_bytes)
-    host_meta[:meta_bytes].copy_(meta[:meta_bytes], non_blocking=True)  # D2H 1: offsets + per-stream status
+    # ONE device-to-host copy in the common case: the metadata plus as many payload bytes as the previous calls needed
+    # per stream (+ 25 %); a second copy fetches the remainder only when a batch codes unusually long strings
+    n_sym = symbols[0].numel()
+    guess = min(out.numel() - meta_al, int(n * ws.bytes_per_stream.get(n_sym, 0.6 * n_sym + 16) * 1.25) + 1024)
+    host = ws.host("host_out", meta_al + guess)
+    host[: meta_al + guess].copy_(out[: meta_al + guess], non_blocking=True)
     stream.synchronize()
-    hm = host_meta.numpy()
-    offs_h = hm[: (n + 1) * 8].view("int64")
-    nb_h = hm[(n + 1) * 8: meta_bytes].view("int32")
+    hv = host.numpy()
+    offs_h = hv[: (n + 1) * 8].view("int64")
+    nb_h = hv[(n + 1) * 8: (n + 1) * 8 + n * 4].view("int32")
     if (nb_h < 0).any():
         bad = [int(i) for i in (nb_h < 0).nonzero()[0][:8]]
         raise ValueError(f"rans_encode: malformed input for streams {bad} (index out of range or zero-width CDF bin)")
     total = int(offs_h[n])
-    host_blob = ws.host("host_blob", total)
-    host_blob[:total].copy_(packed[:total], non_blocking=True)          # D2H 2: exactly the coded bytes
-    stream.synchronize()
-    blob = host_blob.numpy()[:total].tobytes()
+    ws.bytes_per_stream[n_sym] = max(32.0, total / n)
+    if total > guess:
+        host2 = ws.host("host_out2", total)
+        host2[:total].copy_(out[meta_al: meta_al + total], non_blocking=True)
+        stream.synchronize()
+        blob = host2.numpy()[:total].tobytes()
+    else:
+        blob = hv[meta_al: meta_al + total].tobytes()
     cuts = offs_h.tolist()
     return [blob[cuts[i]: cuts[i + 1]] for i in range(n)]
 
