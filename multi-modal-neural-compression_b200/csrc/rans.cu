@@ -8,15 +8,18 @@
 //   tables : the (n_cdfs x stride) int32 CDF table becomes a RAGGED uint16 table once per update() (53 KB for the
 //            64 x 3133 Gaussian table instead of 802 KB): small enough to live in shared memory;
 //   pass 1 (fully parallel, thread <-> symbol): symbol -> (cdf start : 16 | range : 16) and the exact 64-bit reciprocal
-//           of the range, written TRANSPOSED as [position][stream] so that pass 2 reads are coalesced across streams.
-//           The ragged table is staged in shared memory when the batch re-uses it often enough;
-//   pass 2 (thread <-> stream): walks positions last -> first; the state update is a multiply-high + shift instead of
-//           a 64-bit divide and modulo (hd_math.cuh: rans_div), 4 + 8 bytes read per symbol, escapes (rare) re-derive
-//           their payload from the symbol itself; words are pushed backwards into the stream's slab;
-//   compact: exclusive scan of byte counts + gather into one buffer, so the host does one D2H of metadata and one of
-//           bytes.
-// Decoding is thread <-> stream with the ragged table in shared memory and a binary search of the row (CompressAI
-// scans linearly), the stream words prefetched one ahead.
+//           of the range.  The ragged table is staged in shared memory when the batch re-uses it often enough;
+//   pass 2 (WARP <-> stream): walks positions last -> first.  The coder state is a chain of dependent integer
+//           operations, so a stream cannot use more than one thread's worth of arithmetic - but the other 31 lanes
+//           take the memory latency off the chain: the warp fetches 32 staged entries with one coalesced load and
+//           hands them to the (lane-uniform) state update by shuffle.  The update itself is a multiply-high + shift
+//           instead of a 64-bit divide and modulo (hd_math.cuh: rans_div); escapes (rare) re-derive their payload from
+//           the symbol itself; lane 0 pushes the words backwards into the stream's slab;
+//   compact: exclusive scan of byte counts + gather into one buffer, so the host does one D2H.
+// Decoding is WARP <-> stream as well, with the ragged table in shared memory: the 32 lanes probe 32 pivots of the CDF
+// row at once, so a 3133-entry row is resolved in three rounds of (shared load, ballot) instead of twelve dependent
+// binary-search steps (CompressAI scans linearly); CDF indexes are fetched 32 at a time, stream words one ahead,
+// decoded symbols leave in coalesced groups of 32.
 #include "common.cuh"
 #include "hd_math.cuh"
 #include "tma_host.cuh"
@@ -24,9 +27,8 @@
 namespace mmnc {
 
 constexpr int RANS_MAP_THREADS = 256;
-constexpr int RANS_STREAM_THREADS = 32;
 constexpr int RANS_DECODE_THREADS = 128;
-constexpr int RANS_CHUNK = 8;  // independent loads kept in flight per thread in the sequential passes
+constexpr int RANS_WARP_BLOCK = 128;  // sequential passes: one warp per stream, four streams per block
 constexpr size_t RANS_SMEM_TABLE_MAX = 200 * 1024;
 
 struct RansTables {
@@ -42,6 +44,13 @@ __device__ __forceinline__ int32_t stream_index(const int32_t *indexes, int64_t 
                                                 int64_t stream, int64_t n_sym, int64_t pos) {
     if (indexes != nullptr) return indexes[stream * n_sym + pos];
     return (int32_t)((pos / channel_period) % n_cdfs);
+}
+
+// RansEnc::put_bits for the warp-per-stream pass: lane-uniform state, lane 0 stores
+__device__ __forceinline__ void warp_put_bits(uint64_t &x, uint32_t *&ptr, int lane, uint32_t val) {
+    const uint64_t x_max = ((RANS_L >> 16) << 32) * (uint64_t)(1u << (16 - RANS_BYPASS_BITS));
+    if (x >= x_max) { --ptr; if (lane == 0) *ptr = (uint32_t)x; x >>= 32; }
+    x = (x << RANS_BYPASS_BITS) | val;
 }
 
 // ---------------------------------------------------------------------------------------------- ragged tables
@@ -88,8 +97,7 @@ rans_map_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__
     const int64_t total = n_streams * n_sym;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        // i enumerates (position, stream) with stream fastest so that the staging writes are coalesced
-        const int64_t pos = i / n_streams, stream = i - pos * n_streams;
+        const int64_t stream = i / n_sym, pos = i - stream * n_sym;  // staging is [stream][position]
         const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
         uint32_t sr = 0u;
         uint64_t rcp = 0ull;
@@ -111,47 +119,59 @@ rans_map_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- encode, pass 2
-__global__ void __launch_bounds__(RANS_STREAM_THREADS)
+__global__ void __launch_bounds__(RANS_WARP_BLOCK)
 rans_encode_kernel(const uint32_t *__restrict__ stage_sr, const uint64_t *__restrict__ stage_rcp,
                    const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t channel_period,
                    int64_t n_streams, int64_t n_sym, const RansTables tb, uint32_t *__restrict__ slabs,
                    int64_t slab_words, int32_t *__restrict__ nbytes) {
-    const int64_t stream = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (stream >= n_streams) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t stream = (int64_t)blockIdx.x * (RANS_WARP_BLOCK / 32) + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;  // whole warps leave together
     uint32_t *slab = slabs + stream * slab_words;
-    RansEnc enc;
-    enc.init(slab + slab_words);
+    const uint32_t *sr_row = stage_sr + stream * n_sym;
+    const uint64_t *rcp_row = stage_rcp + stream * n_sym;
+    RansEnc enc;  // every lane carries the same state; only lane 0 stores
+    uint32_t *ptr = slab + slab_words;
+    enc.x = RANS_L;
     bool ok = true;
-    // The staging reads do not depend on the coder state: RANS_CHUNK entries are fetched together (one L2 round trip
-    // per chunk instead of one per symbol), then the state chain runs over them.
-    for (int64_t hi = n_sym; hi > 0 && ok; hi -= RANS_CHUNK) {
-        uint32_t sr_c[RANS_CHUNK];
-        uint64_t rcp_c[RANS_CHUNK];
-#pragma unroll
-        for (int k = 0; k < RANS_CHUNK; ++k) {
+    for (int64_t hi = n_sym; hi > 0 && ok; hi -= 32) {
+        // lane l holds the entry of position hi - 1 - l: one coalesced load per 32 symbols
+        const int64_t mine = hi - 1 - lane;
+        const uint32_t sr_l = mine >= 0 ? sr_row[mine] : 0u;
+        const uint64_t rcp_l = mine >= 0 ? rcp_row[mine] : 0ull;
+        const int count = hi < 32 ? (int)hi : 32;
+#pragma unroll 4
+        for (int k = 0; k < count; ++k) {
+            const uint32_t sr = __shfl_sync(0xffffffffu, sr_l, k);
+            const uint64_t rcp = __shfl_sync(0xffffffffu, rcp_l, k);
             const int64_t pos = hi - 1 - k;
-            sr_c[k] = pos >= 0 ? stage_sr[pos * n_streams + stream] : 0u;
-            rcp_c[k] = pos >= 0 ? stage_rcp[pos * n_streams + stream] : 0ull;
-        }
-#pragma unroll
-        for (int k = 0; k < RANS_CHUNK; ++k) {
-            const int64_t pos = hi - 1 - k;
-            if (pos < 0) break;
-            const uint32_t start = sr_c[k] & 0xFFFFu, range = sr_c[k] >> 16;
-            if (range == 0u || enc.ptr - slab < 16) { ok = false; break; }
+            const uint32_t start = sr & 0xFFFFu, range = sr >> 16;
+            if (range == 0u || ptr - slab < 16) { ok = false; break; }
             if (start + range == 65536u) {
                 // the escape slot is the last one of its row; its payload is re-derived from the symbol (rare path)
                 const int32_t ci = stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, pos);
                 uint32_t raw;
                 rans_map_symbol(symbols[stream * n_sym + pos], tb.offsets[ci], tb.sizes[ci] - 2, &raw);
-                rans_put_escape_reversed(enc, raw);
+                const int nb = rans_nibbles(raw);
+                // same order as rans_put_escape_reversed: payload nibbles high -> low, then the count digit(s)
+                for (int j = nb - 1; j >= 0; --j) warp_put_bits(enc.x, ptr, lane, (raw >> (j * RANS_BYPASS_BITS)) & RANS_BYPASS_MAX);
+                const int full = nb / RANS_BYPASS_MAX, rest = nb - full * RANS_BYPASS_MAX;
+                warp_put_bits(enc.x, ptr, lane, (uint32_t)rest);
+                for (int q = 0; q < full; ++q) warp_put_bits(enc.x, ptr, lane, RANS_BYPASS_MAX);
             }
-            enc.put_rcp(start, range, rcp_c[k]);
+            // RansEnc::put_rcp with the store predicated on lane 0
+            const uint64_t x_max = ((RANS_L >> RANS_PRECISION) << 32) * range;
+            if (enc.x >= x_max) { --ptr; if (lane == 0) *ptr = (uint32_t)enc.x; enc.x >>= 32; }
+            const uint64_t q = rans_div(enc.x, range, rcp);
+            enc.x = (q << RANS_PRECISION) + (enc.x - q * range) + start;
         }
     }
+    if (lane != 0) return;
     if (!ok) { nbytes[stream] = -2; return; }
-    enc.flush();
-    nbytes[stream] = (int32_t)((slab + slab_words - enc.ptr) * (int64_t)sizeof(uint32_t));
+    ptr -= 2;
+    ptr[0] = (uint32_t)enc.x;
+    ptr[1] = (uint32_t)(enc.x >> 32);
+    nbytes[stream] = (int32_t)((slab + slab_words - ptr) * (int64_t)sizeof(uint32_t));
 }
 
 // exclusive scan of max(nbytes, 0) into offsets[0..n]; single block of 1024 threads, chunked.  The per-stream byte
@@ -260,6 +280,22 @@ struct RansDecW {
     }
 };
 
+// Slot of `cum` in a ragged row (last s in [0, len - 2] with row[s] <= cum), found by the whole warp: every round the
+// lanes probe 32 evenly spaced pivots of the remaining range and a ballot counts how many lie at or below cum.
+__device__ __forceinline__ int warp_find_slot(const uint16_t *row, int len, uint32_t cum, int lane) {
+    int lo = 0, hi = len - 1;  // invariant: row[lo] <= cum < row[hi], row[len - 1] standing for 65536
+    while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        const int idx = lo + (lane + 1) * step;
+        const bool le = idx < hi && (uint32_t)row[idx] <= cum;
+        const int k = __popc(__ballot_sync(0xffffffffu, le));  // pivots are increasing: the first k lanes say yes
+        const int nlo = lo + k * step;
+        hi = min(hi, nlo + step);
+        lo = nlo;
+    }
+    return lo;
+}
+
 template <bool kSmemTable>
 __global__ void __launch_bounds__(RANS_DECODE_THREADS)
 rans_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restrict__ offsets,
@@ -285,41 +321,40 @@ rans_decode_kernel(const uint8_t *__restrict__ packed, const int64_t *__restrict
         table = reinterpret_cast<const uint16_t *>(rans_smem);
         row_start = small; sizes = small + tb.n_cdfs; offs = small + 2 * tb.n_cdfs;
     }
-    const int64_t stream = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (stream >= n_streams) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t stream = (int64_t)blockIdx.x * (RANS_DECODE_THREADS / 32) + (threadIdx.x >> 5);
+    if (stream >= n_streams) return;  // whole warps leave together (after the block-wide staging barrier)
     const int64_t b0 = offsets[stream];
     const int32_t len_bytes = lengths[stream];
     int32_t st = 0;
-    if (len_bytes < 8 || (len_bytes & 3)) { status[stream] = -1; return; }
-    RansDecW dec;
+    if (len_bytes < 8 || (len_bytes & 3)) { if (lane == 0) status[stream] = -1; return; }
+    RansDecW dec;  // lane-uniform state
     dec.init(reinterpret_cast<const uint32_t *>(packed + b0), reinterpret_cast<const uint32_t *>(packed + b0 + len_bytes));
-    for (int64_t p0 = 0; p0 < n_sym && st == 0; p0 += RANS_CHUNK) {
-        // the CDF indexes do not depend on the decoder state: fetch a chunk, then run the state chain over it
-        int32_t ci_c[RANS_CHUNK];
-#pragma unroll
-        for (int k = 0; k < RANS_CHUNK; ++k)
-            ci_c[k] = (p0 + k < n_sym) ? stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, p0 + k) : 0;
-#pragma unroll
-        for (int k = 0; k < RANS_CHUNK; ++k) {
-            const int64_t pos = p0 + k;
-            if (pos >= n_sym) break;
-            const int32_t ci = ci_c[k];
+    int32_t *out_row = symbols + stream * n_sym;
+    for (int64_t p0 = 0; p0 < n_sym && st == 0; p0 += 32) {
+        // the CDF indexes do not depend on the decoder state: one coalesced load per 32 symbols
+        const int32_t ci_l = (p0 + lane < n_sym) ? stream_index(indexes, channel_period, tb.n_cdfs, stream, n_sym, p0 + lane) : 0;
+        const int count = (n_sym - p0 < 32) ? (int)(n_sym - p0) : 32;
+        int32_t mine = 0;
+        for (int k = 0; k < count; ++k) {
+            const int32_t ci = __shfl_sync(0xffffffffu, ci_l, k);
             if (ci < 0 || ci >= tb.n_cdfs) { st = -3; break; }
             const int32_t len = sizes[ci];
             const int32_t max_value = len - 2;
             if (max_value < 0) { st = -4; break; }
             const uint16_t *row = table + row_start[ci];
-            const int slot = rans_find_slot_u16(row, len, dec.peek());
+            const int slot = warp_find_slot(row, len, dec.peek(), lane);
             if (slot < 0 || slot > max_value) { st = -4; break; }
             const uint32_t start = row[slot];
             dec.advance(start, ((uint32_t)row[slot + 1] - start) & 0xFFFFu);
             int32_t value = slot;
             if (slot == max_value) value = dec.get_escape(max_value);
-            symbols[stream * n_sym + pos] = value + offs[ci];
+            if (lane == k) mine = value + offs[ci];
             if (dec.overrun) { st = -2; break; }
         }
+        if (st == 0 && lane < count) out_row[p0 + lane] = mine;  // 32 decoded symbols leave together
     }
-    status[stream] = st;
+    if (lane == 0) status[stream] = st;
 }
 
 static RansTables make_tables(const uint16_t *ragged, int64_t ragged_len, const int32_t *row_start,
@@ -390,9 +425,9 @@ extern "C" int mmnc_rans_encode_batch(const int32_t *symbols, const int32_t *ind
         }
         if (int rc = after_launch("rans_map_kernel")) return rc;
     }
-    rans_encode_kernel<<<(unsigned)((n_streams + RANS_STREAM_THREADS - 1) / RANS_STREAM_THREADS),
-                         RANS_STREAM_THREADS, 0, s>>>(stage_sr, stage_rcp, symbols, indexes, channel_period, n_streams,
-                                                      n_sym, tb, slabs, slab_words, nbytes);
+    constexpr int per_block = RANS_WARP_BLOCK / 32;
+    rans_encode_kernel<<<(unsigned)((n_streams + per_block - 1) / per_block), RANS_WARP_BLOCK, 0, s>>>(
+        stage_sr, stage_rcp, symbols, indexes, channel_period, n_streams, n_sym, tb, slabs, slab_words, nbytes);
     return after_launch("rans_encode_kernel");
 }
 
@@ -430,7 +465,8 @@ extern "C" int mmnc_rans_decode_batch(const uint8_t *packed, const int64_t *offs
                  "rans_decode_batch: ragged table must be 16-byte aligned, packed 4-byte aligned");
     const RansTables tb = make_tables(ragged_cdf, ragged_len, row_start, cdf_sizes, cdf_offsets, n_cdfs);
     const size_t table_bytes = ((size_t)ragged_len + 7) / 8 * 16 + (size_t)n_cdfs * 12;
-    const unsigned blocks = (unsigned)((n_streams + RANS_DECODE_THREADS - 1) / RANS_DECODE_THREADS);
+    constexpr int per_block = RANS_DECODE_THREADS / 32;  // one warp per stream
+    const unsigned blocks = (unsigned)((n_streams + per_block - 1) / per_block);
     // the row search is a chain of dependent loads: from shared memory unless the table is too large for it or the
     // batch is so small that copying the table costs more than it saves
     const bool smem_table = table_bytes <= RANS_SMEM_TABLE_MAX && n_sym * 12 >= (int64_t)(table_bytes / 2048);
