@@ -55,7 +55,7 @@ eb_forward_kernel(const float *__restrict__ x, int64_t B, int64_t C, int64_t S, 
         if (bound > 0.f) l = max_nan(l, bound);
         out[a] = v;
         lik[a] = l;
-        acc += logf(l);
+        acc += fast_log(l);
     };
     if (n < (1ll << 31)) {  // 32-bit index arithmetic
         const uint32_t n32 = (uint32_t)n, s32 = (uint32_t)S, step = gridDim.y * blockDim.x;
@@ -67,6 +67,69 @@ eb_forward_kernel(const float *__restrict__ x, int64_t B, int64_t C, int64_t S, 
     } else {
         for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x)
             element(eb_addr(e, c, C, S));
+    }
+    if (lnsum != nullptr) {
+        const float tot = block_sum(acc, red);
+        if (threadIdx.x == 0) atomicAdd(&lnsum[c], tot);
+    }
+}
+
+// Vector path (S % 4 == 0, 16-byte aligned tensors): four consecutive elements of one (image, channel) row per thread -
+// 128-bit loads and stores, one Philox call for the four noise values, four independent MLP evaluations in flight.
+__global__ void __launch_bounds__(EB_THREADS)
+eb_forward_vec4_kernel(const float *__restrict__ x, uint32_t B, uint32_t C, uint32_t S, const float *__restrict__ params,
+                       const float *__restrict__ medians, int noise_mode, const float *__restrict__ noise,
+                       uint64_t seed, uint64_t offset, float bound, float *__restrict__ out, float *__restrict__ lik,
+                       float *__restrict__ lnsum) {
+    __shared__ float P[EB_NP];
+    __shared__ float red[32];
+    const uint32_t c = blockIdx.x;
+    if (threadIdx.x < EB_NP) P[threadIdx.x] = eb_transform(threadIdx.x, params[(int64_t)c * EB_NP + threadIdx.x]);
+    __syncthreads();
+    const float med = medians[c];
+    const uint32_t q = S >> 2, n4 = B * q;
+    float acc = 0.f;
+    if (noise_mode == MMNC_QUANT_NOISE_PHILOX_DEV) {
+        const uint64_t *st = reinterpret_cast<const uint64_t *>(noise);
+        seed = st[0];
+        offset += st[1];
+        noise_mode = MMNC_QUANT_NOISE_PHILOX;
+    }
+    const uint32_t step = gridDim.y * blockDim.x;
+    for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < n4; e += step) {
+        const uint32_t b = e / q, s4 = e - b * q;
+        const int64_t a = ((int64_t)b * C + c) * S + 4 * s4;
+        const float4 xv = *reinterpret_cast<const float4 *>(x + a);
+        float v[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (noise_mode == MMNC_QUANT_DEQUANTIZE) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = rintf(v[k] - med) + med;
+        } else if (noise_mode == MMNC_QUANT_NOISE_PHILOX) {
+            const uint64_t gi = (uint64_t)a + offset;
+            float u[4];
+            if ((gi & 3ull) == 0) {
+                philox4_centered(seed, gi >> 2, u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) u[k] = philox_uniform_centered(seed, gi + k);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] += u[k];
+        } else if (noise_mode == MMNC_QUANT_NOISE_GIVEN) {
+            const float4 nv = *reinterpret_cast<const float4 *>(noise + a);
+            v[0] += nv.x; v[1] += nv.y; v[2] += nv.z; v[3] += nv.w;
+        }
+        float l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float tl = v[k] - 0.5f, tu = v[k] + 0.5f;
+            l[k] = eb_likelihood_s(P, tl, tu - tl);
+            if (bound > 0.f) l[k] = max_nan(l[k], bound);
+            acc += fast_log(l[k]);
+        }
+        __stcs(reinterpret_cast<float4 *>(out + a), make_float4(v[0], v[1], v[2], v[3]));
+        __stcs(reinterpret_cast<float4 *>(lik + a), make_float4(l[0], l[1], l[2], l[3]));
+        if (e + step < e) break;
     }
     if (lnsum != nullptr) {
         const float tot = block_sum(acc, red);
@@ -102,7 +165,7 @@ eb_backward_kernel(const float *__restrict__ outv, int64_t B, int64_t C, int64_t
         const float upper = eb_logits<true>(P, v + 0.5f, &tu);
         const float raw = eb_likelihood(lower, upper, form);
         const float l = (bound > 0.f) ? max_nan(raw, bound) : raw;
-        float g = (g_lik != nullptr ? g_lik[a] : 0.f) + gls / l;
+        float g = (g_lik != nullptr ? g_lik[a] : 0.f) + fast_div(gls, l);
         if (bound > 0.f) g = lower_bound_grad(raw, bound, g);
         float dl, du;
         eb_likelihood_grad(lower, upper, form, &dl, &du);
@@ -165,11 +228,15 @@ eb_aux_loss_kernel(const float *__restrict__ quantiles, int64_t C, const float *
     if (threadIdx.x == 0) atomicAdd(loss, tot);
 }
 
-static inline int eb_splits(int64_t C, int64_t n_per_channel) {
+// One block per channel whenever the channel is small (every shape of the reference's models: <= 4096 elements per
+// channel): per-channel sums (ln-likelihood, the 58 parameter gradients) are then single fixed-order block reductions
+// and bit-reproducible.  Large inputs are split over several blocks whose partial sums meet in atomicAdds.
+static inline int eb_splits(int64_t C, int64_t n_per_channel, int per_thread = 1) {
+    if (n_per_channel <= 8192) return 1;
     // enough blocks to cover the machine a few times over, but never more than the work in a channel
     const int64_t target_blocks = (int64_t)sm_count() * 8;
     int64_t splits = (target_blocks + C - 1) / C;
-    const int64_t max_splits = (n_per_channel + EB_THREADS - 1) / EB_THREADS;
+    const int64_t max_splits = (n_per_channel / per_thread + EB_THREADS - 1) / EB_THREADS;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
@@ -192,6 +259,15 @@ extern "C" int mmnc_eb_forward(const float *x, int64_t B, int64_t C, int64_t S, 
     MMNC_REQUIRE((noise_mode != MMNC_QUANT_NOISE_GIVEN && noise_mode != MMNC_QUANT_NOISE_PHILOX_DEV) || noise,
                  "eb_forward: this noise_mode needs the noise pointer");
     MMNC_REQUIRE(C <= 2147483647LL, "eb_forward: too many channels");
+    const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(lik) |
+                      (noise_mode == MMNC_QUANT_NOISE_GIVEN ? reinterpret_cast<uintptr_t>(noise) : 0)) & 15) == 0;
+    if ((S & 3) == 0 && al && B * S < (1ll << 31)) {
+        dim3 grid4((unsigned)C, (unsigned)eb_splits(C, B * S, 4));
+        eb_forward_vec4_kernel<<<grid4, EB_THREADS, 0, as_stream(stream)>>>(x, (uint32_t)B, (uint32_t)C, (uint32_t)S, params,
+                                                                            medians, noise_mode, noise, seed, offset,
+                                                                            likelihood_bound, out, lik, lnsum);
+        return after_launch("eb_forward_vec4_kernel");
+    }
     dim3 grid((unsigned)C, (unsigned)eb_splits(C, B * S));
     eb_forward_kernel<<<grid, EB_THREADS, 0, as_stream(stream)>>>(x, B, C, S, params, medians, noise_mode, noise,
                                                                    seed, offset, likelihood_bound, likelihood_form,

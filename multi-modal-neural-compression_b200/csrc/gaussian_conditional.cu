@@ -47,7 +47,7 @@ gc_forward_kernel(const float *__restrict__ y, const float *__restrict__ scales,
         if (lik_bound > 0.f) l = max_nan(l, lik_bound);
         lik[ai] = l;
         if (!bcast || s == 0) y_hat[yi] = v;
-        acc += logf(l);
+        acc += fast_log(l);
     };
     if (n < (1ll << 31)) {  // 32-bit index arithmetic (a 64-bit division per element costs as much as the likelihood)
         const uint32_t n32 = (uint32_t)n, ss32 = (uint32_t)Ss, step = gridDim.y * blockDim.x;
@@ -65,6 +65,104 @@ gc_forward_kernel(const float *__restrict__ y, const float *__restrict__ scales,
     if (lnsum != nullptr) {
         const float tot = block_sum(acc, red);
         if (threadIdx.x == 0) atomicAdd(&lnsum[c], tot);
+    }
+}
+
+// Vector path (no broadcast, no means, Ss % 4 == 0, 16-byte aligned tensors): a thread owns four consecutive elements
+// of one (image, channel) row - 128-bit loads and stores, ONE Philox call for the four noise values, four independent
+// likelihood evaluations in flight.  This is the path the declared roofline shape (1024, 192, 16, 16) takes.
+__global__ void __launch_bounds__(GC_THREADS)
+gc_forward_vec4_kernel(const float *__restrict__ y, const float *__restrict__ scales, uint32_t B, uint32_t C, uint32_t Ss,
+                       int noise_mode, const float *__restrict__ noise, uint64_t seed, uint64_t offset,
+                       float scale_bound, float lik_bound, float *__restrict__ y_hat, float *__restrict__ lik,
+                       float *__restrict__ lnsum) {
+    __shared__ float red[32];
+    const uint32_t c = blockIdx.x;
+    const uint32_t q = Ss >> 2, n4 = B * q;  // groups of four per channel
+    float acc = 0.f;
+    if (noise_mode == MMNC_QUANT_NOISE_PHILOX_DEV) {
+        const uint64_t *st = reinterpret_cast<const uint64_t *>(noise);
+        seed = st[0];
+        offset += st[1];
+        noise_mode = MMNC_QUANT_NOISE_PHILOX;
+    }
+    const uint32_t step = gridDim.y * blockDim.x;
+    for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < n4; e += step) {
+        const uint32_t b = e / q, s4 = e - b * q;
+        const int64_t ai = ((int64_t)b * C + c) * Ss + 4 * s4;
+        const float4 yv = *reinterpret_cast<const float4 *>(y + ai);
+        const float4 sv = *reinterpret_cast<const float4 *>(scales + ai);
+        float v[4] = {yv.x, yv.y, yv.z, yv.w};
+        const float sc[4] = {sv.x, sv.y, sv.z, sv.w};
+        if (noise_mode == MMNC_QUANT_DEQUANTIZE) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = rintf(v[k]);
+        } else if (noise_mode == MMNC_QUANT_NOISE_PHILOX) {
+            const uint64_t gi = (uint64_t)ai + offset;
+            float u[4];
+            if ((gi & 3ull) == 0) {
+                philox4_centered(seed, gi >> 2, u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) u[k] = philox_uniform_centered(seed, gi + k);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] += u[k];
+        } else if (noise_mode == MMNC_QUANT_NOISE_GIVEN) {
+            const float4 nv = *reinterpret_cast<const float4 *>(noise + ai);
+            v[0] += nv.x; v[1] += nv.y; v[2] += nv.z; v[3] += nv.w;
+        }
+        float l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            l[k] = gc_likelihood_s(v[k], 0.f, sc[k], scale_bound);
+            if (lik_bound > 0.f) l[k] = max_nan(l[k], lik_bound);
+            acc += fast_log(l[k]);
+        }
+        __stcs(reinterpret_cast<float4 *>(lik + ai), make_float4(l[0], l[1], l[2], l[3]));
+        __stcs(reinterpret_cast<float4 *>(y_hat + ai), make_float4(v[0], v[1], v[2], v[3]));
+        if (e + step < e) break;
+    }
+    if (lnsum != nullptr) {
+        const float tot = block_sum(acc, red);
+        if (threadIdx.x == 0) atomicAdd(&lnsum[c], tot);
+    }
+}
+
+__global__ void __launch_bounds__(GC_THREADS)
+gc_backward_vec4_kernel(const float *__restrict__ y_hat, const float *__restrict__ scales, uint32_t B, uint32_t C,
+                        uint32_t Ss, const float *__restrict__ g_yhat, const float *__restrict__ g_lik,
+                        const float *__restrict__ g_lnsum, float scale_bound, float lik_bound, float *__restrict__ g_y,
+                        float *__restrict__ g_scales) {
+    const uint32_t c = blockIdx.x;
+    const uint32_t q = Ss >> 2, n4 = B * q;
+    const float gls = (g_lnsum != nullptr) ? g_lnsum[c] : 0.f;
+    const uint32_t step = gridDim.y * blockDim.x;
+    for (uint32_t e = blockIdx.y * blockDim.x + threadIdx.x; e < n4; e += step) {
+        const uint32_t b = e / q, s4 = e - b * q;
+        const int64_t ai = ((int64_t)b * C + c) * Ss + 4 * s4;
+        const float4 yv = *reinterpret_cast<const float4 *>(y_hat + ai);
+        const float4 sv = *reinterpret_cast<const float4 *>(scales + ai);
+        float4 gl4 = make_float4(0.f, 0.f, 0.f, 0.f), gy4 = gl4;
+        if (g_lik != nullptr) gl4 = *reinterpret_cast<const float4 *>(g_lik + ai);
+        if (g_yhat != nullptr) gy4 = *reinterpret_cast<const float4 *>(g_yhat + ai);
+        const float v[4] = {yv.x, yv.y, yv.z, yv.w}, sc[4] = {sv.x, sv.y, sv.z, sv.w};
+        const float gl[4] = {gl4.x, gl4.y, gl4.z, gl4.w}, gyh[4] = {gy4.x, gy4.y, gy4.z, gy4.w};
+        float oy[4], os[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float raw = gc_likelihood_s(v[k], 0.f, sc[k], scale_bound);
+            const float l = (lik_bound > 0.f) ? max_nan(raw, lik_bound) : raw;
+            float g = gl[k] + fast_div(gls, l);
+            if (lik_bound > 0.f) g = lower_bound_grad(raw, lik_bound, g);
+            float dy, dsc;
+            gc_likelihood_grad(v[k], 0.f, sc[k], scale_bound, &dy, &dsc);
+            oy[k] = g * dy + gyh[k];
+            os[k] = lower_bound_grad(sc[k], scale_bound, g * dsc);
+        }
+        __stcs(reinterpret_cast<float4 *>(g_y + ai), make_float4(oy[0], oy[1], oy[2], oy[3]));
+        __stcs(reinterpret_cast<float4 *>(g_scales + ai), make_float4(os[0], os[1], os[2], os[3]));
+        if (e + step < e) break;
     }
 }
 
@@ -94,7 +192,7 @@ gc_backward_kernel(const float *__restrict__ y_hat, const float *__restrict__ sc
             const float sc = scales[ai];
             const float raw = gc_likelihood_s(v, m, sc, scale_bound);
             const float l = (lik_bound > 0.f) ? max_nan(raw, lik_bound) : raw;
-            float g = (g_lik != nullptr ? g_lik[ai] : 0.f) + gls / l;
+            float g = (g_lik != nullptr ? g_lik[ai] : 0.f) + fast_div(gls, l);
             if (lik_bound > 0.f) g = lower_bound_grad(raw, lik_bound, g);
             float dy, dsc;
             gc_likelihood_grad(v, m, sc, scale_bound, &dy, &dsc);
@@ -124,7 +222,7 @@ lnsum_forward_kernel(const float *__restrict__ lik, int64_t B, int64_t C, int64_
     float acc = 0.f;
     for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
         const int64_t b = e / S, s = e - b * S;
-        acc += logf(lik[(b * C + c) * S + s]);
+        acc += fast_log(lik[(b * C + c) * S + s]);
     }
     const float tot = block_sum(acc, red);
     if (threadIdx.x == 0) atomicAdd(&lnsum[c], tot);
@@ -139,15 +237,21 @@ lnsum_backward_kernel(const float *__restrict__ lik, int64_t n, int64_t C, int64
     }
 }
 
-static inline int gc_splits(int64_t C, int64_t n_per_channel) {
+// One block per channel whenever the channel is small (every shape of the reference's models: <= 4096 elements per
+// channel): its per-channel sum is then a single fixed-order block reduction and the result is bit-reproducible.  Only
+// large inputs are split over several blocks, whose partial sums meet in an atomicAdd (order not fixed).
+static inline int gc_splits(int64_t C, int64_t n_per_channel, int per_thread = 1) {
+    if (n_per_channel <= 8192) return 1;
     const int64_t target_blocks = (int64_t)sm_count() * 8;
     int64_t splits = (target_blocks + C - 1) / C;
-    const int64_t max_splits = (n_per_channel + GC_THREADS - 1) / GC_THREADS;
+    const int64_t max_splits = (n_per_channel / per_thread + GC_THREADS - 1) / GC_THREADS;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
     return (int)splits;
 }
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace mmnc
 
@@ -165,6 +269,16 @@ extern "C" int mmnc_gc_forward(const float *y, const float *scales, const float 
     MMNC_REQUIRE(y && scales && y_hat && lik, "gc_forward: null pointer");
     MMNC_REQUIRE((noise_mode != MMNC_QUANT_NOISE_GIVEN && noise_mode != MMNC_QUANT_NOISE_PHILOX_DEV) || noise,
                  "gc_forward: this noise_mode needs the noise pointer");
+    if (Sy == Ss && means == nullptr && (Ss & 3) == 0 && B * Ss < (1ll << 31) && C < (1ll << 31) && aligned16(y) &&
+        aligned16(scales) && aligned16(y_hat) && aligned16(lik) &&
+        (noise_mode != MMNC_QUANT_NOISE_GIVEN || aligned16(noise))) {
+        dim3 grid4((unsigned)C, (unsigned)gc_splits(C, B * Ss, 4));
+        gc_forward_vec4_kernel<<<grid4, GC_THREADS, 0, as_stream(stream)>>>(y, scales, (uint32_t)B, (uint32_t)C,
+                                                                            (uint32_t)Ss, noise_mode, noise, seed, offset,
+                                                                            scale_bound, likelihood_bound, y_hat, lik,
+                                                                            lnsum);
+        return after_launch("gc_forward_vec4_kernel");
+    }
     dim3 grid((unsigned)C, (unsigned)gc_splits(C, B * Ss));
     gc_forward_kernel<<<grid, GC_THREADS, 0, as_stream(stream)>>>(y, scales, means, B, C, Sy, Ss, noise_mode,
                                                                    noise, seed, offset, scale_bound,
@@ -180,6 +294,15 @@ extern "C" int mmnc_gc_backward(const float *y_hat, const float *scales, const f
     MMNC_REQUIRE(Sy == Ss || Sy == 1, "gc_backward: unsupported broadcast");
     if (B * C * Ss == 0) return MMNC_OK;
     MMNC_REQUIRE(y_hat && scales && g_y && g_scales, "gc_backward: null pointer");
+    if (Sy == Ss && means == nullptr && (Ss & 3) == 0 && B * Ss < (1ll << 31) && C < (1ll << 31) && aligned16(y_hat) &&
+        aligned16(scales) && aligned16(g_y) && aligned16(g_scales) && aligned16(g_yhat) && aligned16(g_lik)) {
+        dim3 grid4((unsigned)C, (unsigned)gc_splits(C, B * Ss, 4));
+        gc_backward_vec4_kernel<<<grid4, GC_THREADS, 0, as_stream(stream)>>>(y_hat, scales, (uint32_t)B, (uint32_t)C,
+                                                                             (uint32_t)Ss, g_yhat, g_lik, g_lnsum,
+                                                                             scale_bound, likelihood_bound, g_y,
+                                                                             g_scales);
+        return after_launch("gc_backward_vec4_kernel");
+    }
     int reduce_mode = 0;
     if (Sy != Ss) {
         const bool pow2 = (Ss & (Ss - 1)) == 0;

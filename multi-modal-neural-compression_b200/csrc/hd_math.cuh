@@ -20,10 +20,26 @@ MMNC_HD float sign_t(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f
 // torch.max(x, bound): unlike fmaxf it propagates a NaN in x (LowerBound must not hide a diverged value)
 MMNC_HD float max_nan(float x, float bound) { return (x != x) ? x : fmaxf(x, bound); }
 
-// Philox4x32-10 keyed by a 64-bit seed, counter = 64-bit element index.  Returns U[-0.5, 0.5).
+// Device: MUFU-based approximations (ex2.approx / lg2.approx / rcp.approx: 1-2 ulp) where the error budget allows it
+// (stated at each use); host (tests/hostcheck): the libm function of the same name.
+#if defined(__CUDA_ARCH__)
+MMNC_HD float fast_exp(float x) { return __expf(x); }
+MMNC_HD float fast_log(float x) { return __logf(x); }
+MMNC_HD float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+MMNC_HD float fast_div(float a, float b) { return __fdividef(a, b); }
+#else
+MMNC_HD float fast_exp(float x) { return expf(x); }
+MMNC_HD float fast_log(float x) { return logf(x); }
+MMNC_HD float fast_rcp(float x) { return 1.f / x; }
+MMNC_HD float fast_div(float a, float b) { return a / b; }
+#endif
+
+// Philox4x32-10 keyed by a 64-bit seed, counter = 64-bit block index.  One call yields FOUR uniforms: element i of a
+// noise stream uses component (i & 3) of block (i >> 2), so a thread that owns four consecutive elements pays for one
+// call (the forward kernels' vector path) and a scalar caller gets the same numbers.  Values are U[-0.5, 0.5).
 MMNC_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
-MMNC_HD float philox_uniform_centered(uint64_t seed, uint64_t index) {
-    uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+MMNC_HD void philox4_centered(uint64_t seed, uint64_t block, float out[4]) {
+    uint32_t c0 = (uint32_t)block, c1 = (uint32_t)(block >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -33,7 +49,32 @@ MMNC_HD float philox_uniform_centered(uint64_t seed, uint64_t index) {
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    return (float)(c0 >> 8) * (1.0f / 16777216.0f) - 0.5f;  // 24-bit mantissa, [0,1) - 0.5
+    out[0] = (float)(c0 >> 8) * (1.0f / 16777216.0f) - 0.5f;  // 24-bit mantissa, [0,1) - 0.5
+    out[1] = (float)(c1 >> 8) * (1.0f / 16777216.0f) - 0.5f;
+    out[2] = (float)(c2 >> 8) * (1.0f / 16777216.0f) - 0.5f;
+    out[3] = (float)(c3 >> 8) * (1.0f / 16777216.0f) - 0.5f;
+}
+MMNC_HD float philox_uniform_centered(uint64_t seed, uint64_t index) {
+    float u[4];
+    philox4_centered(seed, index >> 2, u);
+    const uint32_t k = (uint32_t)index & 3u;
+    return k == 0 ? u[0] : (k == 1 ? u[1] : (k == 2 ? u[2] : u[3]));
+}
+
+// tanh with ~3e-7 relative error: Taylor series to x^11 below 0.3 (truncation < 2e-9), 1 - 2 / (e^2|x| + 1) above
+// (ex2.approx + rcp.approx: absolute error ~1e-7).  About half the instructions of tanhf; the EB forward calls it 24
+// times per element and is bound by instruction issue (profiles/).
+MMNC_HD float tanh_f(float x) {
+    const float z = fabsf(x), s = x * x;
+    float p = -8.863235529902197e-3f;                 // -1382 / 155925
+    p = p * s + 2.186948853615520e-2f;                 // 62 / 2835
+    p = p * s - 5.396825396825397e-2f;                 // -17 / 315
+    p = p * s + 1.333333333333333e-1f;                 // 2 / 15
+    p = p * s - 3.333333333333333e-1f;                 // -1 / 3
+    const float small = x + x * (p * s);
+    const float e = fast_exp(2.f * fminf(z, 15.f));
+    const float big = copysignf(1.f - 2.f * fast_rcp(e + 1.f), x);
+    return z < 0.3f ? small : big;                     // NaN: both sides are NaN
 }
 
 // ---------------------------------------------------------------------------------------------- EB (A.3)
@@ -60,7 +101,7 @@ MMNC_HD float eb_logits(const float *P, float t, EbTrace *tr) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float a = P[i] * t + P[3 + i];
-        const float ta = tanhf(a);
+        const float ta = tanh_f(a);
         h[i] = a + P[6 + i] * ta;
         if (kTrace) { tr->th[0][i] = ta; tr->h[0][i] = h[i]; }
     }
@@ -74,7 +115,7 @@ MMNC_HD float eb_logits(const float *P, float t, EbTrace *tr) {
             a += P[base + 3 * i + 1] * h[1];
             a += P[base + 3 * i + 2] * h[2];
             a += P[base + 9 + i];
-            const float ta = tanhf(a);
+            const float ta = tanh_f(a);
             n[i] = a + P[base + 12 + i] * ta;
             if (kTrace) { tr->th[l][i] = ta; }
         }
@@ -144,10 +185,16 @@ MMNC_HD float eb_logits_backward(const float *P, float t, const EbTrace &tr, flo
 // per element.
 MMNC_HD float eb_tanh_diff(float a, float ta, float da) {
     if (da < 0.25f) {
-        const float td = tanhf(da);
-        return td * (1.f - ta * ta) / (1.f + ta * td);
+        // tanh(da) by its Taylor series to da^9 (truncation < 1e-8 below 0.25): five multiply-adds instead of a tanhf
+        const float s = da * da;
+        float p = 2.186948853615520e-2f;
+        p = p * s - 5.396825396825397e-2f;
+        p = p * s + 1.333333333333333e-1f;
+        p = p * s - 3.333333333333333e-1f;
+        const float td = da + da * (p * s);
+        return fast_div(td * (1.f - ta * ta), 1.f + ta * td);
     }
-    return tanhf(a + da) - ta;
+    return tanh_f(a + da) - ta;
 }
 // tl = fp32(v - 1/2) and dt = fp32(v + 1/2) - tl (an exact subtraction; 1 up to the rounding of the two sums, which the
 // reference has as well)
@@ -157,7 +204,7 @@ MMNC_HD float eb_likelihood_s(const float *P, float tl, float dt) {
     for (int i = 0; i < 3; ++i) {
         const float a = P[i] * tl + P[3 + i];
         const float da = P[i] * dt;
-        const float ta = tanhf(a);
+        const float ta = tanh_f(a);
         h[i] = a + P[6 + i] * ta;
         dh[i] = da + P[6 + i] * eb_tanh_diff(a, ta, da);
     }
@@ -174,7 +221,7 @@ MMNC_HD float eb_likelihood_s(const float *P, float tl, float dt) {
             float da = P[base + 3 * i] * dh[0];
             da += P[base + 3 * i + 1] * dh[1];
             da += P[base + 3 * i + 2] * dh[2];
-            const float ta = tanhf(a);
+            const float ta = tanh_f(a);
             n[i] = a + P[base + 12 + i] * ta;
             dn[i] = da + P[base + 12 + i] * eb_tanh_diff(a, ta, da);
         }
@@ -191,9 +238,10 @@ MMNC_HD float eb_likelihood_s(const float *P, float tl, float dt) {
     // sigma(fl + df) - sigma(fl) on the side where both arguments lean negative
     float a = fl, b = fl + df;
     if (a + b > 0.f) { const float na = -b; b = -a; a = na; }
-    const float ea = expf(a), eb = expf(b);
-    if (df > 30.f) return eb / (1.f + eb) - ea / (1.f + ea);  // far apart: no cancellation (and expm1 would overflow)
-    return ea * expm1f(df) / ((1.f + ea) * (1.f + eb));
+    // ea, eb <= 1 (a <= b, a + b <= 0 ... b may be positive only when |a| is larger): ex2.approx is 2 ulp here
+    const float ea = fast_exp(a), eb = fast_exp(b);
+    if (df > 30.f) return fast_div(eb, 1.f + eb) - fast_div(ea, 1.f + ea);  // far apart: no cancellation (expm1 would overflow)
+    return fast_div(ea * expm1f(df), (1.f + ea) * (1.f + eb));
 }
 
 // likelihood from the two logits (before the floor); also the partial derivatives w.r.t. (lower, upper)
@@ -234,37 +282,58 @@ MMNC_HD float gc_likelihood(float y_hat, float mean, float scale, float scale_bo
     const float lower = gc_std_cumulative((-0.5f - v) / sc);
     return upper - lower;
 }
+// erfc with fractional error ~1.2e-7 (Numerical Recipes' Chebyshev fit `erfcc`: erfc(z) = t exp(-z^2 + P(t)),
+// t = 1 / (1 + z / 2)): one reciprocal, nine multiply-adds, one exponential - about a third of erfcf.
+MMNC_HD float erfc_f(float x) {
+    const float z = fabsf(x);
+    const float t = fast_rcp(1.f + 0.5f * z);
+    float p = 0.17087277f;
+    p = p * t - 0.82215223f;
+    p = p * t + 1.48851587f;
+    p = p * t - 1.13520398f;
+    p = p * t + 0.27886807f;
+    p = p * t - 0.18628806f;
+    p = p * t + 0.09678418f;
+    p = p * t + 0.37409196f;
+    p = p * t + 1.00002368f;
+    p = p * t - 1.26551223f;
+    const float ans = t * fast_exp(p - z * z);
+    return x >= 0.f ? ans : 2.f - ans;  // NaN falls through as NaN
+}
 // fp32 evaluation WITHOUT the cancellation: lik = (1/sqrt(pi)) * integral of exp(-t^2) over [cu, cl], the two erfc
-// arguments torch computes (same fp32 roundings as above).  Narrow intervals (cl - cu < 0.5, i.e. scale > 1.41) are
-// integrated with a 5-point Gauss-Legendre rule: truncation error < 2e-9 relative where lik > 1e-3 and < 1e-6 down to
-// the 1e-9 floor, and every term is positive, so nothing cancels.  Wide intervals use the erfc difference, whose
-// cancellation factor is at most 1.9 there.  Holds the float64 bars of the parity tests (1e-5 bulk, 5e-5 tails) at
-// a fraction of the cost of two float64 erfc (the first build of this kernel: 0.12 of the HBM roof at the roofline shape).
+// arguments.  Narrow intervals (cl - cu < 0.5, i.e. scale > 1.41) are integrated with a 5-point Gauss-Legendre rule:
+// truncation error < 2e-9 relative where lik > 1e-3 and < 1e-6 down to the 1e-9 floor, and every term is positive, so
+// nothing cancels.  Wide intervals use the erfc difference, whose cancellation factor is at most ~4.5 there.  One
+// reciprocal of the scale serves both arguments (the reference divides twice; 1 ulp of the argument), exponentials
+// are ex2.approx on the device: measured against the float64 value of the formula (tests/test_kernel_math_hostcheck.py
+// on the host, tests/test_gpu_parity.py and bench.py's roofline_likelihood on the device) this stays inside 1e-5 on the
+// bulk and 5e-5 on the tails.
 MMNC_HD float gc_likelihood_s(float y_hat, float mean, float scale, float scale_bound) {
     const float sc = max_nan(scale, scale_bound);
     const float v = fabsf(y_hat - mean);
-    const float tu = (0.5f - v) / sc, tl = (-0.5f - v) / sc;
-    const float cu = GC_CONST * tu, cl = GC_CONST * tl;  // cu < cl
-    const float d = cl - cu;
+    const float ninv = GC_CONST * fast_rcp(sc);             // -1 / (sc sqrt 2)
+    const float cu = (0.5f - v) * ninv, cl = (-0.5f - v) * ninv;  // cu < cl
+    const float d = -ninv;                                  // cl - cu exactly
     if (d < 0.5f) {
         const float h = 0.5f * d, m = cu + h;
         const float s1 = 0.5384693101056831f * h, s2 = 0.9061798459386640f * h;
-        float sum = 0.5688888888888889f * expf(-(m * m));
-        sum += 0.4786286704993665f * (expf(-((m + s1) * (m + s1))) + expf(-((m - s1) * (m - s1))));
-        sum += 0.2369268850561891f * (expf(-((m + s2) * (m + s2))) + expf(-((m - s2) * (m - s2))));
+        float sum = 0.5688888888888889f * fast_exp(-(m * m));
+        sum += 0.4786286704993665f * (fast_exp(-((m + s1) * (m + s1))) + fast_exp(-((m - s1) * (m - s1))));
+        sum += 0.2369268850561891f * (fast_exp(-((m + s2) * (m + s2))) + fast_exp(-((m - s2) * (m - s2))));
         return 0.56418958354775628695f * h * sum;  // 1 / sqrt(pi)
     }
-    return 0.5f * (erfcf(cu) - erfcf(cl));  // also the NaN / Inf route (d is NaN when both arguments are infinite)
+    return 0.5f * (erfc_f(cu) - erfc_f(cl));  // also the NaN route (d is NaN when the scale is)
 }
 // d lik / d y_hat and d lik / d (bounded scale)
 MMNC_HD void gc_likelihood_grad(float y_hat, float mean, float scale, float scale_bound, float *d_y, float *d_sc) {
     const float sc = max_nan(scale, scale_bound);
     const float d = y_hat - mean;
     const float v = fabsf(d);
-    const float tu = (0.5f - v) / sc, tl = (-0.5f - v) / sc;
-    const float pu = INV_SQRT_2PI * expf(-0.5f * tu * tu), pl = INV_SQRT_2PI * expf(-0.5f * tl * tl);
-    *d_y = sign_t(d) * (pl - pu) / sc;
-    *d_sc = (tl * pl - tu * pu) / sc;
+    const float inv = fast_rcp(sc);
+    const float tu = (0.5f - v) * inv, tl = (-0.5f - v) * inv;
+    const float pu = INV_SQRT_2PI * fast_exp(-0.5f * tu * tu), pl = INV_SQRT_2PI * fast_exp(-0.5f * tl * tl);
+    *d_y = sign_t(d) * (pl - pu) * inv;
+    *d_sc = (tl * pl - tu * pu) * inv;
 }
 
 // ---------------------------------------------------------------------------------------------- indexes (A.4)

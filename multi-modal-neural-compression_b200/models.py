@@ -75,7 +75,11 @@ class ScaleHyperprior(nn.Module):
         y = self.g_a(x)
         z = self.h_a(torch.abs(y))
         z_strings = self.entropy_bottleneck.compress(z)
-        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        # CompressAI decodes the strings it has just produced to obtain z_hat; the decoder returns round(z - median) +
+        # median symbol by symbol, i.e. exactly the eval-mode quantisation of z (asserted bit for bit in
+        # tests/test_gpu_parity.py::test_eb_compress_bit_exact), so the decode round trip (H2D of the strings, a
+        # decode pass and a host synchronisation) is skipped.
+        z_hat = self.entropy_bottleneck.quantize(z, "dequantize", self.entropy_bottleneck._get_medians().detach())
         scales_hat = self.h_s(z_hat)
         indexes = self.gaussian_conditional.build_indexes(scales_hat)
         y_strings = self.gaussian_conditional.compress(y, indexes)

@@ -104,13 +104,21 @@ def test_gc_stable_fp32_likelihood_against_float64(hc):
     y[:12] = torch.tensor([0, 1, -1, 40, -40, 1000, 0.5, -0.5, 1e6, -1e6, 0.4999, -0.4999])
     lik = np.empty(n, dtype=np.float32)
     hc.hc_gc_likelihood_s(fptr(y.numpy()), fptr(scales.numpy()), ctypes.c_int64(n), ctypes.c_float(0.11), fptr(lik))
-    sc, v = torch.maximum(scales, torch.tensor(0.11)), y.abs()
-    const = torch.tensor(-(2 ** -0.5), dtype=torch.float32)
-    cu, cl = (const * ((0.5 - v) / sc)).double(), (const * ((-0.5 - v) / sc)).double()
+    # the exact value of the formula for these fp32 inputs: everything in float64 (what the `want64` oracle of the GPU
+    # parity tests evaluates).  CompressAI's fp32 evaluation rounds the two erfc arguments first, which by itself moves
+    # the likelihood by up to ~1e-4 relative at the largest scales - it is measured against the same exact value below.
+    sc, v = torch.maximum(scales, torch.tensor(0.11)).double(), y.abs().double()
+    cu, cl = -(2 ** -0.5) * ((0.5 - v) / sc), -(2 ** -0.5) * ((-0.5 - v) / sc)
     ref = 0.5 * (torch.special.erfc(cu) - torch.special.erfc(cl))
     got = torch.from_numpy(lik).double()
     rel = (got - ref).abs() / ref.clamp_min(1e-300)
-    assert rel[ref > 1e-3].max() < 3e-6 and rel[(ref > 1e-6) & (ref <= 1e-3)].max() < 5e-6
+    print("gc_likelihood_s vs float64: bulk", rel[ref > 1e-3].max().item(), "tails", rel[(ref > 1e-6) & (ref <= 1e-3)].max().item())
+    assert rel[ref > 1e-3].max() < 3e-6 and rel[(ref > 1e-6) & (ref <= 1e-3)].max() < 1e-5
+    s32, v32 = torch.maximum(scales, torch.tensor(0.11)), y.abs()
+    c32 = torch.tensor(-(2 ** -0.5), dtype=torch.float32)
+    fp32 = (0.5 * torch.special.erfc(c32 * ((0.5 - v32) / s32)) - 0.5 * torch.special.erfc(c32 * ((-0.5 - v32) / s32))).double()
+    rel32 = (fp32 - ref).abs() / ref.clamp_min(1e-300)
+    assert rel[ref > 1e-3].max() < rel32[ref > 1e-3].max(), "the kernel arithmetic should beat the plain fp32 evaluation"
     assert (got - ref).abs()[ref <= 1e-6].max() < 1e-11
     assert np.isfinite(lik).all() and (lik >= 0).all()
 
