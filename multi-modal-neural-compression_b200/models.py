@@ -79,7 +79,8 @@ class ScaleHyperprior(nn.Module):
         # median symbol by symbol, i.e. exactly the eval-mode quantisation of z (asserted bit for bit in
         # tests/test_gpu_parity.py::test_eb_compress_bit_exact), so the decode round trip (H2D of the strings, a
         # decode pass and a host synchronisation) is skipped.
-        z_hat = self.entropy_bottleneck.quantize(z, "dequantize", self.entropy_bottleneck._get_medians().detach())
+        z_hat = self.entropy_bottleneck.quantize(
+            z, "dequantize", self.entropy_bottleneck._get_medians().detach().reshape(1, -1, *([1] * (z.dim() - 2))))
         scales_hat = self.h_s(z_hat)
         indexes = self.gaussian_conditional.build_indexes(scales_hat)
         y_strings = self.gaussian_conditional.compress(y, indexes)
