@@ -53,6 +53,9 @@ int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, 
 bool gdn_tc_forward2_supported(const float *x, const float *y, int64_t B, int64_t C, int64_t HW);
 // gdn_tc_bwd2.cu
 bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64_t C, int64_t HW);
+bool gdn_tc_backward2_streams(int64_t C);
+int gdn_tc_backward2(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
+                     float *, void *, size_t, cudaStream_t);
 // gdn_tc_bwd.cu
 bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW);
 size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW);
@@ -106,6 +109,7 @@ extern "C" size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_
     (void)precision;
     if (B <= 0 || C <= 0 || HW <= 0) return 256;
     if (gdn_small_supported(C)) return gdn_small_backward_workspace(B, C, HW);
+    // the caller may not know yet whether its tensors will be aligned for the TMA-fed kernel: cover every candidate
     const size_t a = gdn_simt_backward_workspace(B, C, HW), b = gdn_tc_backward_workspace(B, C, HW);
     const bool tc = (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW);
     return tc ? b : (a > b ? a : b);
@@ -114,8 +118,10 @@ extern "C" size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_
 extern "C" int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t B, int64_t C, int64_t HW,
                                          int precision) {
     if (gdn_small_supported(C)) return 0;
-    if ((precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW))
-        return gdn_tc_backward2_supported(x, g, B, C, HW) ? 3 : 2;
+    if (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) {
+        if (gdn_tc_backward2_supported(x, g, B, C, HW)) return gdn_tc_backward2_streams(C) ? 4 : 3;
+        if (gdn_tc_backward_supported(B, C, HW)) return 2;
+    }
     return 1;
 }
 
@@ -147,9 +153,14 @@ static int gdn_backward_impl(const float *x, const float *g, int64_t B, int64_t 
     if (gdn_small_supported(C))
         return gdn_small_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
                                   as_stream(stream));
-    if ((precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW))
-        return gdn_tc_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
-                               as_stream(stream));
+    if (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) {
+        if (gdn_tc_backward2_supported(x, g, B, C, HW))  // TMA-fed: C <= 128, H*W a multiple of 128, aligned tensors
+            return gdn_tc_backward2(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+                                    as_stream(stream));
+        if (gdn_tc_backward_supported(B, C, HW))
+            return gdn_tc_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+                                   as_stream(stream));
+    }
     return gdn_simt_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
                              as_stream(stream));
 }

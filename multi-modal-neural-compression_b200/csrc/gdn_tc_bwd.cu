@@ -385,9 +385,9 @@ size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW) {
     int P;
     uint32_t cols;
     size_t smem;
-    if (!tcb_geometry(C, &P, &cols, &smem)) return 0;
+    const size_t v2 = gdn_tc_backward2_workspace(B, C, HW);  // also covers the wide layers only the TMA-fed kernel takes
+    if (!tcb_geometry(C, &P, &cols, &smem)) return v2;
     const size_t v1 = sizeof(float) * (size_t)tcb_grid(B * HW, cols, smem) * C * (C + 1) + 256;
-    const size_t v2 = gdn_tc_backward2_workspace(B, C, HW);
     return v1 > v2 ? v1 : v2;
 }
 

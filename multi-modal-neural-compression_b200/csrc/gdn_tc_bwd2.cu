@@ -20,6 +20,11 @@
 //   * no global-load address arithmetic or load latency in the compute warps; every loop invariant lives in shared
 //     memory, descriptors are assembled inside the MMA asm blocks: no spills (see Bwd2Ctx and tc_ptx.cuh for why
 //     that matters more than usual here).
+//   * wide layers (112 <= C <= 128: gamma and gamma^T would take 166 KB next to a 139 KB landing stage) STREAM the
+//     contraction operand: one shared-memory buffer holds gamma for MMA1 and is refilled with gamma^T for MMA2 (and
+//     back) by cp.async.bulk copies of a pre-packed image of both tiles (a small pack kernel writes them, already in
+//     the core-matrix layout, into the workspace: 2 x 81 KB that stay in L2).  The refill is issued by the leader the
+//     moment the MMA that read the buffer has retired and lands behind the epilogue that follows.
 // Requires HW % 128 == 0 (a 128-pixel tile never straddles two images) and 16-byte aligned tensors; everything else
 // stays on gdn_tc_bwd.cu.
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
@@ -49,10 +54,27 @@ struct Bwd2Ctx {
     uint32_t stage0;         // shared address of stage 0 ([u | x2] per stage, R8 * 4096 bytes each)
     uint32_t gamma0;         // shared address of the gamma tile; gamma^T follows P * P * 4 bytes later
     uint32_t full_bar0, mma_bar0, free_bar0;  // shared addresses of the mbarrier arrays
+    uint32_t bfull;          // (streamed operand) shared address of the "gamma buffer filled" mbarrier
     uint32_t tmem_base;
     const void *tm_x, *tm_g;
+    const float *bsrc;       // (streamed operand) packed gamma tile in global memory; gamma^T follows P * P floats later
     float *dx;
 };
+
+// Streamed operand: refill the single gamma buffer with tile `which` (0 = gamma, 1 = gamma^T) of the packed image.
+template <int P>
+__device__ __forceinline__ void bwd2_load_b(const volatile Bwd2Ctx &t, int which) {
+    constexpr uint32_t BYTES = (uint32_t)(P * P * 4), PIECE = BYTES / 4;  // P is a multiple of 16: PIECE % 256 == 0
+    static_assert(P % 16 == 0, "four 16-byte aligned pieces");
+    const uint32_t bar = t.bfull, dst = t.gamma0;
+    const uint64_t src = reinterpret_cast<uint64_t>(t.bsrc) + (uint64_t)which * BYTES;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(BYTES) : "memory");
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + i * PIECE), "l"(src + i * PIECE), "r"(PIECE), "r"(bar)
+                     : "memory");
+}
 
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
     uint32_t done = 0;
@@ -141,7 +163,7 @@ __device__ __forceinline__ void tmem_stw(uint32_t taddr, const uint32_t (&r)[W])
 // the instruction footprint inside the instruction cache (ncu: 21 % of the stalls were instruction fetches with two
 // copies).  Channel offsets are folded into the per-thread TMEM / shared / global bases; only the last 16 channels of
 // a thread can be padding, and a 16-bit mask says which.
-template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse>
+template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse, bool kStream>
 __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int group, int tg, uint32_t tmem_base_in) {
     using namespace tc;
     using namespace tcb2;
@@ -238,6 +260,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         // ---- MMA1: D = x2 * gamma^T (+ beta through the constant column)
         if (leader) {
             fence_after();
+            if constexpr (kStream) mbar_wait_addr(t.bfull, 0u);  // fills alternate gamma (phase 0) / gamma^T (phase 1)
             mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0, 128), GAMMA_HI, IDESC);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
             // A refill that could not be issued at the end of the previous tile (its MMA3 had not retired yet) is
@@ -258,6 +281,8 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         mbar_wait_addr(mbar, parity);
         parity ^= 1;
         fence_after();
+        // MMA1 has retired: the buffer it read is refilled with gamma^T while epilogue 1 runs
+        if (kStream && leader) bwd2_load_b<P>(t, 1);
         // ---- epilogue 1: u -> A (TMEM) and over g in the landing buffer (MMA3's A operand); f = g n^p kept for later
         MMNC_FRESH_OI();
 #pragma unroll
@@ -297,7 +322,8 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         //      MMA3: D3 += u^T x2 (K = 128 pixels of this stage), committed to the "stage free" barrier
         if (leader) {
             fence_after();
-            mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0 + (uint32_t)(P * P * 4), 128), GAMMA_HI, IDESC);
+            if constexpr (kStream) mbar_wait_addr(t.bfull, 1u);
+            mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0 + (kStream ? 0u : (uint32_t)(P * P * 4)), 128), GAMMA_HI, IDESC);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
             mma_ss_chain<0>(tmem_base + (uint32_t)(NGROUPS * 2 * P + group * P), desc_lo(us, 16), desc_lo(xs, 16), PIX_HI,
                             (uint32_t)t.R8 * 64u, IDESC, first ? 0u : 1u);
@@ -306,6 +332,9 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         mbar_wait_addr(mbar, parity);
         parity ^= 1;
         fence_after();
+        // MMA2 has retired: gamma comes back for the next tile's MMA1 while epilogue 2 runs (nothing is left in flight
+        // when the CTA has no further tile)
+        if (kStream && leader && k + NGROUPS < t.n_k) bwd2_load_b<P>(t, 0);
         // ---- epilogue 2: dx = g n^p + 2 x t
         bool refilled = false;
         {
@@ -366,11 +395,11 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     return first;
 }
 
-template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse>
+template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse, bool kStream>
 __global__ void __launch_bounds__(NGROUPS * TPP * 128, 1)
 gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                         int ntiles, int tiles_per_img, int HW, const GdnParams prm, float *__restrict__ dx,
-                        float *__restrict__ part, int C, uint32_t tmem_cols) {
+                        float *__restrict__ part, int C, uint32_t tmem_cols, const float *__restrict__ packed_b) {
     using namespace tc;
     using namespace tcb2;
     constexpr int P = KH8 * 16;
@@ -380,6 +409,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     __shared__ uint64_t full_bar[2 * NSTAGES];  // [stage][x, g]
     __shared__ uint64_t mma_bar[NGROUPS];
     __shared__ uint64_t free_bar[NGROUPS];
+    __shared__ uint64_t bfull_bar;
     __shared__ uint32_t tmem_base_s;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int R8 = (C + 1 + 7) >> 3;
@@ -396,6 +426,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         for (int s = 0; s < 2 * NSTAGES; ++s) mbar_init(&full_bar[s], 1);
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&mma_bar[q], 1);
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&free_bar[q], 1);
+        mbar_init(&bfull_bar, 1);
         tma_prefetch_desc(&tm_x);
         tma_prefetch_desc(&tm_g);
         Bwd2Ctx c;
@@ -408,8 +439,10 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         c.full_bar0 = smem_u32(&full_bar[0]);
         c.mma_bar0 = smem_u32(&mma_bar[0]);
         c.free_bar0 = smem_u32(&free_bar[0]);
+        c.bfull = smem_u32(&bfull_bar);
         c.tmem_base = 0;  // read from tmem_base_s once the allocation is visible
         c.tm_x = &tm_x; c.tm_g = &tm_g;
+        c.bsrc = packed_b;
         c.dx = dx;
         ctx_s = c;
     }
@@ -421,13 +454,14 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const int n_k = ctx.n_k;
         const int pre = n_k < NSTAGES ? n_k : NSTAGES;
         for (int k = 0; k < pre; ++k) bwd2_issue_tile<NSTAGES>(ctx, k);
+        if (kStream && n_k > 0) bwd2_load_b<P>(ctx, 0);  // gamma for the first MMA1
     }
     // gamma tiles, as in gdn_tc_bwd.cu: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]); column k = C holds beta
     // Loads first (eight elements = sixteen loads per thread in flight), then the arithmetic: one dependent L2 round
     // trip per element made this loop ~30 us per CTA at C = 100.
     constexpr int kcores = P >> 2;
     constexpr int SU = 8;
-    for (int base = threadIdx.x; base < P * P; base += THREADS * SU) {
+    for (int base = threadIdx.x; base < (kStream ? 0 : P * P); base += THREADS * SU) {  // streamed: packed by a kernel
         float raw[SU], rawt[SU];
 #pragma unroll
         for (int u = 0; u < SU; ++u) {
@@ -475,7 +509,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     fence_before();
     __syncthreads();
     fence_after();
-    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, TPP, kInverse>(ctx, group, tg, tmem_base_s);
+    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, TPP, kInverse, kStream>(ctx, group, tg, tmem_base_s);
     // ---- this group's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
     float *dst = part + ((int64_t)blockIdx.x * NGROUPS + group) * C * (C + 1);
     const int pix = tg & 127;
@@ -503,6 +537,24 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     if (warp == 0) tmem_dealloc(tmem_base_s, tmem_cols);
 }
 
+// Streamed operand: both contraction tiles in the K-major core-matrix layout the MMAs read, written once per call.
+//   out[0 .. P*P)      gamma   (N = out channel i, K = in channel j); column K = C holds beta, rows >= C hold 1 there
+//   out[P*P .. 2 P*P)  gamma^T (N = in channel k, K = out channel i)
+__global__ void __launch_bounds__(256)
+gdn_pack_gamma_kernel(const GdnParams prm, int C, int P, uint32_t *__restrict__ out) {
+    const int kcores = P >> 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P * P; idx += gridDim.x * blockDim.x) {
+        const int n = idx / P, k = idx - n * P;
+        float v = 0.f, vt = 0.f;
+        if (n < C && k < C) { v = prm.g(n * C + k); vt = prm.g(k * C + n); }
+        else if (n < C && k == C) v = prm.b(n);
+        else if (n >= C && k == C) v = 1.f;  // padded outputs get norm = 1 (finite)
+        const int off = (((n >> 3) * kcores + (k >> 2)) << 5) + ((n & 7) << 2) + (k & 3);
+        out[off] = tc::to_tf32(v);
+        out[P * P + off] = tc::to_tf32(vt);
+    }
+}
+
 // fixed-order reduction of per-group partials [ksplit][C][C+1] -> d gamma, d beta (gdn_simt.cu)
 int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &prm, float *dgamma, float *dbeta,
                         cudaStream_t s);
@@ -510,18 +562,21 @@ int gdn_reduce_partials(const float *part, int ksplit, int C, const GdnParams &p
 // ------------------------------------------------------------------------------------------------------ host side
 struct Bwd2Geometry {
     int P, groups, stages;
+    bool stream;          // one gamma buffer refilled from a packed global image instead of two resident tiles
     uint32_t tmem_cols;
     size_t smem;
 };
 
 static bool bwd2_geometry(int64_t C, Bwd2Geometry *g) {
-    if (C < 16 || C > 111) return false;
+    if (C < 16 || C > 128) return false;
     const int P = (int)((C + 1 + 15) / 16 * 16);
     const size_t R8 = (size_t)(C + 1 + 7) / 8;
-    const size_t stage = 2 * R8 * 4096, gam = 2 * (size_t)P * P * 4;
+    g->stream = C > 111;
+    const size_t stage = 2 * R8 * 4096, gam = (g->stream ? 1 : 2) * (size_t)P * P * 4;
     const size_t budget = 227 * 1024 - 1024 - 256;  // alignment slack + static shared memory
     // two groups need x and g of a tile in 128 registers per thread: P <= 64 (32 channels per thread)
     int groups = (P <= 64) ? 2 : 1;
+    if (g->stream && stage + gam > budget) return false;
     int stages = 0;
     for (;;) {
         const int want = (groups == 2) ? 3 : 2;
@@ -572,11 +627,17 @@ bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64
     return tmah::encode_tiled() != nullptr;
 }
 
+bool gdn_tc_backward2_streams(int64_t C) {
+    Bwd2Geometry geo;
+    return bwd2_geometry(C, &geo) && geo.stream;
+}
+
 size_t gdn_tc_backward2_workspace(int64_t B, int64_t C, int64_t HW) {
     Bwd2Geometry geo;
     if (!bwd2_geometry(C, &geo)) return 0;
     (void)B; (void)HW;
-    return sizeof(float) * (size_t)sm_count() * geo.groups * C * (C + 1) + 256;
+    const size_t packed = geo.stream ? 2 * sizeof(float) * (size_t)geo.P * geo.P + 256 : 0;
+    return sizeof(float) * (size_t)sm_count() * geo.groups * C * (C + 1) + 256 + packed;
 }
 
 static int make_map(CUtensorMap *m, const float *p, int64_t B, int64_t C, int64_t HW) {
@@ -601,13 +662,14 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     if (int rc = make_map(&tm_x, x, B, C, HW)) return rc;
     if (int rc = make_map(&tm_g, g, B, C, HW)) return rc;
     using Kernel = void (*)(const CUtensorMap, const CUtensorMap, int, int, int, const GdnParams, float *, float *,
-                            int, uint32_t);
+                            int, uint32_t, const float *);
     Kernel kernel = nullptr;
     // two threads per pixel everywhere: four (1024 threads x 64 registers on the two-group instances, 512 x 128 with f
     // parked in TMEM on the single-group ones) was measured slower on every layer shape (see the kernel's comment)
     const int tpp = 2;
-#define MMNC_PICK(N, G, S) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, true> : (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, false>)
-    const int key = (geo.P / 16) * 100 + geo.groups * 10 + geo.stages;
+#define MMNC_PICK(N, G, S) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, true, false> : (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, false, false>)
+#define MMNC_PICK_STREAM(N) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, 1, 1, 2, true, true> : (Kernel)gdn_tc_backward2_kernel<N, 1, 1, 2, false, true>)
+    const int key = (geo.stream ? 1000 : 0) + (geo.P / 16) * 100 + geo.groups * 10 + geo.stages;
     switch (key) {
         case 223: kernel = MMNC_PICK(2, 2, 3); break;
         case 323: kernel = MMNC_PICK(3, 2, 3); break;
@@ -615,9 +677,12 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
         case 512: kernel = MMNC_PICK(5, 1, 2); break;
         case 611: kernel = MMNC_PICK(6, 1, 1); break;
         case 711: kernel = MMNC_PICK(7, 1, 1); break;
+        case 1811: kernel = MMNC_PICK_STREAM(8); break;   // C = 112 .. 127
+        case 1911: kernel = MMNC_PICK_STREAM(9); break;   // C = 128
         default: break;
     }
 #undef MMNC_PICK
+#undef MMNC_PICK_STREAM
     if (kernel == nullptr) {
         set_error("gdn_tc_backward2: no kernel instance for C = %lld (P %d, groups %d, stages %d)", (long long)C, geo.P,
                   geo.groups, geo.stages);
@@ -625,8 +690,20 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     }
     if (int rc = tmah::ensure_dynamic_smem(kernel, geo.smem)) return rc;
     float *part = static_cast<float *>(workspace);
+    const float *packed_b = nullptr;
+    if (geo.stream) {
+        // the packed tiles live behind the partials (128-byte aligned: the bulk copies need 16)
+        const size_t part_bytes = (sizeof(float) * (size_t)ksplit * C * (C + 1) + 127) / 128 * 128;
+        const size_t need = part_bytes + 2 * sizeof(float) * (size_t)geo.P * geo.P;
+        MMNC_REQUIRE(workspace_bytes >= need, "gdn_backward: workspace too small for the packed gamma tiles");
+        MMNC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "gdn_backward: workspace must be 16-byte aligned");
+        uint32_t *dst = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + part_bytes);
+        gdn_pack_gamma_kernel<<<(geo.P * geo.P + 255) / 256, 256, 0, s>>>(prm, (int)C, geo.P, dst);
+        if (int rc = after_launch("gdn_pack_gamma_kernel")) return rc;
+        packed_b = reinterpret_cast<const float *>(dst);
+    }
     kernel<<<(unsigned)grid, geo.groups * tpp * 128, geo.smem, s>>>(tm_x, tm_g, (int)ntiles, (int)(HW / tcb2::TILE), (int)HW,
-                                                                   prm, dx, part, (int)C, geo.tmem_cols);
+                                                                   prm, dx, part, (int)C, geo.tmem_cols, packed_b);
     if (int rc = after_launch("gdn_tc_backward2_kernel")) return rc;
     return gdn_reduce_partials(part, ksplit, (int)C, prm, dgamma, dbeta, s);
 }

@@ -61,20 +61,15 @@ MMNC_HD float philox_uniform_centered(uint64_t seed, uint64_t index) {
     return k == 0 ? u[0] : (k == 1 ? u[1] : (k == 2 ? u[2] : u[3]));
 }
 
-// tanh with ~3e-7 relative error: Taylor series to x^11 below 0.3 (truncation < 2e-9), 1 - 2 / (e^2|x| + 1) above
-// (ex2.approx + rcp.approx: absolute error ~1e-7).  About half the instructions of tanhf; the EB forward calls it 24
-// times per element and is bound by instruction issue (profiles/).
+// tanh(x) = 1 - 2 / (e^2x + 1) in five instructions (ex2.approx + rcp.approx), ABSOLUTE error ~1.5e-7 everywhere
+// (the relative error grows as 1e-7 / |x| towards 0, where tanhf switches to a polynomial at five times the cost).
+// The bottleneck network only ever uses tanh additively (h + factor tanh(h), 1 - tanh^2), so the absolute error is
+// what reaches the likelihood: measured <= 2e-6 relative on the likelihood (tests/test_kernel_math_hostcheck.py,
+// bench.py roofline_likelihood).  The EB kernels evaluate 24 of these per element and are bound by instruction issue
+// (profiles/), not by HBM.  Saturates correctly: e = inf -> 1, e = 0 -> -1; NaN propagates.
 MMNC_HD float tanh_f(float x) {
-    const float z = fabsf(x), s = x * x;
-    float p = -8.863235529902197e-3f;                 // -1382 / 155925
-    p = p * s + 2.186948853615520e-2f;                 // 62 / 2835
-    p = p * s - 5.396825396825397e-2f;                 // -17 / 315
-    p = p * s + 1.333333333333333e-1f;                 // 2 / 15
-    p = p * s - 3.333333333333333e-1f;                 // -1 / 3
-    const float small = x + x * (p * s);
-    const float e = fast_exp(2.f * fminf(z, 15.f));
-    const float big = copysignf(1.f - 2.f * fast_rcp(e + 1.f), x);
-    return z < 0.3f ? small : big;                     // NaN: both sides are NaN
+    const float e = fast_exp(2.f * x);
+    return 1.f - 2.f * fast_rcp(e + 1.f);
 }
 
 // ---------------------------------------------------------------------------------------------- EB (A.3)

@@ -423,6 +423,40 @@ def test_gdn_backward_tensor_core_pipelined(shape, inverse):
     assert close(ours.gamma.grad, refd.gamma.grad, 2e-3)
 
 
+@pytest.mark.parametrize("shape", [(6, 128, 64, 64), (3, 128, 128, 128), (10, 112, 32, 32), (5, 120, 64, 32),
+                                   (4, 127, 32, 64), (300, 128, 8, 16), (1, 128, 16, 8)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_backward_tensor_core_streamed_gamma(shape, inverse):
+    """112 <= C <= 128 (BASELINE configs C3 / C4: GDN(128)): the TMA-fed fused backward with the gamma operand streamed
+    through one shared-memory buffer (variant 4), against the float64 oracle at the TF32 bar (2e-3 of the largest
+    entry), deterministic run to run; 96-600 tiles on 148 CTAs, so CTAs with 0, 1 and several tiles all occur."""
+    torch.manual_seed(19)
+    C = shape[1]
+    ours, ref = _pair_gdn(C, inverse, precision="tf32")
+    refd = R.GDN(C, inverse=inverse).double()
+    refd.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
+    x, g = torch.randn(*shape), torch.randn(*shape)
+    xd, gd = x.to(DEV).requires_grad_(True), g.to(DEV)
+    assert _gdn_bwd_variant(xd, gd) == 4, "shape should take the streamed-gamma kernel"
+    before = mm.launch_count()
+    ours(xd).backward(gd)
+    torch.cuda.synchronize()
+    assert mm.launch_count() - before == 1 + 3  # forward; pack gamma tiles, fused backward, partial reduce
+    x64 = x.double().requires_grad_(True)
+    refd(x64).backward(g.double())
+
+    def close(a, b, tol):
+        return ((a.cpu().double() - b).abs().max() / b.abs().max()).item() <= tol
+
+    assert close(xd.grad, x64.grad, 2e-3), ((xd.grad.cpu().double() - x64.grad).abs().max(), x64.grad.abs().max())
+    assert close(ours.beta.grad, refd.beta.grad, 2e-3)
+    assert close(ours.gamma.grad, refd.gamma.grad, 2e-3)
+    first = (xd.grad.clone(), ours.beta.grad.clone(), ours.gamma.grad.clone())
+    xd.grad, ours.beta.grad, ours.gamma.grad = None, None, None
+    ours(xd).backward(gd)
+    assert all(torch.equal(a, b) for a, b in zip(first, (xd.grad, ours.beta.grad, ours.gamma.grad)))
+
+
 @pytest.mark.parametrize("shape", [(32, 50, 128, 128), (16, 100, 128, 128), (24, 64, 128, 128)])
 def test_gdn_backward_pipelined_long_sequences(shape):
     """Dozens of tiles per CTA (every stage and mbarrier phase wraps many times): the pipelined kernel against the
