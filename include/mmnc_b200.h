@@ -196,6 +196,16 @@ int mmnc_nonneg_reparam_backward(const float *p, const float *g_out, int64_t n, 
                                  void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * (f2) step metrics — `average_metrics`, mtc.py:359-384.  PSNR of the regression tasks comes from the distortion
+ *   kernel (PSNR = -10 log10(MSE) for images scaled by 255 with data_range 255); the semantic task's metrics are
+ *   computed on the argmax class-id image: logits (B, K, S) -> labels (B, 1, S) as floats (may be NULL) and
+ *   *sse += sum (argmax - target)^2 (target (B, 1, S) class ids as floats; sse zero-initialised by the caller; both
+ *   may be NULL when only the labels are wanted).  Ties: first maximum, like torch.argmax.
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_argmax_sse(const float *logits, const float *target, int64_t B, int K, int64_t S, float *labels,
+                    float *sse, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * (a9) compressai._CXX.pmf_to_quantized_cdf(pmf: List[float], precision) -> List[int]  — HOST function
  *   (called once per table row from EntropyBottleneck.update / GaussianConditional.update, reference call site
  *   mtc.py:486-489, off the per-step path).  pmf_h: n floats; cdf_h: n + 1 uint32, strictly increasing,

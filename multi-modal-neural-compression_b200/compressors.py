@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import metrics as _metrics
 from . import ops
 from .layers import GDN, conv, deconv
 from .models import ScaleHyperprior, get_scale_table
@@ -105,6 +106,12 @@ class MultiTaskCompressor(nn.Module):
         # bucket), grad_sync() is called between backward() and optimizer.step()
         self.grad_sync = None
         self.grad_zero = None
+        # step metrics (mtc.py:92, 359-384, 468): the reference evaluates PSNR and MS-SSIM of every task on EVERY step.
+        # Validation steps do the same here; training steps every `train_metrics_every` steps (0 = never, 1 = the
+        # reference's behaviour) - MS-SSIM is ~40 filtering passes per task and is not part of the loss.
+        self.metrics = ("psnr", "ms-ssim")
+        self.train_metrics_every = 0
+        self._train_steps = 0
 
     def get_model_name(self):
         return self.__class__.__name__
@@ -286,6 +293,13 @@ class MultiTaskCompressor(nn.Module):
         self._compression_logs(logs, log_dir, names, s[4:4 + inv.numel()], s[3])
         return loss, logs
 
+    # ------------------------------------------------------------------ metrics (mtc.py:359-384)
+    def average_metrics(self, x, x_hats, log_dir: str, task_losses=None) -> Dict[str, torch.Tensor]:
+        """PSNR / MS-SSIM per task, same log names as the reference.  `task_losses` = {task: distortion term} lets the
+        PSNR of the mse tasks reuse the sums the loss already reduced."""
+        return _metrics.average_metrics(self.tasks, x, x_hats, log_dir, task_losses,
+                                        with_ms_ssim="ms-ssim" in self.metrics)
+
     # ------------------------------------------------------------------ optimisation (mtc.py:386-418)
     def auxiliary_loss(self):
         return self.model["compressor"].entropy_bottleneck.loss()
@@ -339,6 +353,12 @@ class MultiTaskCompressor(nn.Module):
             aux_loss.backward()
             aux_opt.step()
             self.lr_schedulers().step()
+            self._train_steps += 1
+        every = self.train_metrics_every if is_train else 1
+        if self.metrics and every and (not is_train or self._train_steps % every == 0):
+            reuse = {t: log_dict[f"{log_dir}/{t}/mse"] for t in self.tasks
+                     if task_parameters[t]["loss_function"] == "mse" and f"{log_dir}/{t}/mse" in log_dict}
+            log_dict.update(self.average_metrics(batch, x_hats, log_dir, reuse))
         self.last_logs = log_dict
         return loss
 
