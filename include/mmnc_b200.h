@@ -206,6 +206,19 @@ int mmnc_argmax_sse(const float *logits, const float *target, int64_t B, int K, 
                     float *sse, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * (f4) input pipeline — what `get_transform` does per sample on the host (src/datasets/transforms.py:39-131,
+ *   src/datasets/clevr.py:48-83), as three kernels over a whole batch of raw decoded pixels:
+ *   u8 HWC (B, HW, src_channels) -> f32 (B, dst_channels, HW), value / divisor (255 for ToTensor);
+ *   u16 (n) -> f32 (n), value / divisor (2^15 - 1 for the 16-bit depth maps);
+ *   labels: channel `channel` of u8 HWC pixels through a 256-entry float table (class remapping of `semantic`).
+ * ------------------------------------------------------------------------------------------------------- */
+int mmnc_prep_u8_hwc_to_f32_chw(const uint8_t *src, int64_t B, int64_t HW, int src_channels, int dst_channels,
+                                float divisor, float *dst, void *stream);
+int mmnc_prep_u16_to_f32(const uint16_t *src, int64_t n, float divisor, float *dst, void *stream);
+int mmnc_prep_labels(const uint8_t *src, int64_t n_pixels, int src_channels, int channel, const float *lut256,
+                     float *dst, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * (a9) compressai._CXX.pmf_to_quantized_cdf(pmf: List[float], precision) -> List[int]  — HOST function
  *   (called once per table row from EntropyBottleneck.update / GaussianConditional.update, reference call site
  *   mtc.py:486-489, off the per-step path).  pmf_h: n floats; cdf_h: n + 1 uint32, strictly increasing,

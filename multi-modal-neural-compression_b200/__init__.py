@@ -4,7 +4,10 @@ Python/PyTorch host code over hand-written sm_100a CUDA kernels behind a C ABI (
 The directory name is not a Python identifier; import it through the `mmnc_b200` alias at the repository root
 (`import mmnc_b200 as mm`).  All sub-modules are imported eagerly so attribute access works through the alias.
 """
-from . import _lib, ops, entropy_models, layers, models, metrics, compressors, parallel, synthetic  # noqa: F401
+from . import (_lib, ops, entropy_models, layers, models, metrics, container, compressors, parallel, synthetic,  # noqa: F401
+               input_pipeline)
+from .container import Container  # noqa: F401
+from .input_pipeline import GpuBatchLoader  # noqa: F401
 from ._lib import build, launch_count  # noqa: F401
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional, LowerBound  # noqa: F401
 from .layers import GDN, NonNegativeParametrizer, conv, deconv  # noqa: F401

@@ -60,6 +60,9 @@ SIGNATURES = {
     "mmnc_nonneg_reparam_forward": (I32, [VP, I64, F32, F32, VP, VP]),
     "mmnc_nonneg_reparam_backward": (I32, [VP, VP, I64, F32, VP, VP]),
     "mmnc_argmax_sse": (I32, [VP, VP, I64, I32, I64, VP, VP, VP]),
+    "mmnc_prep_u8_hwc_to_f32_chw": (I32, [VP, I64, I64, I32, I32, F32, VP, VP]),
+    "mmnc_prep_u16_to_f32": (I32, [VP, I64, F32, VP, VP]),
+    "mmnc_prep_labels": (I32, [VP, I64, I32, I32, VP, VP, VP]),
     "mmnc_pmf_to_quantized_cdf_h": (I32, [ctypes.POINTER(ctypes.c_float), I32, I32, ctypes.POINTER(ctypes.c_uint32)]),
     "mmnc_build_indexes": (I32, [VP, I64, VP, I32, F32, VP, VP]),
     "mmnc_rans_slab_words": (I64, [I64]),

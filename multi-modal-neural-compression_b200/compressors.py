@@ -195,8 +195,17 @@ class MultiTaskCompressor(nn.Module):
         return torch.concat(self._run_heads([(lambda i=i, t=t: heads[i](batch[t])) for i, t in enumerate(self.tasks)]),
                             dim=1)
 
-    def forward_output_heads(self, stacked_latent_values):
+    def _head_input(self, stacked_latent_values, i: int, task: str) -> torch.Tensor:
+        """What output head i reads of the decoded latent (all of it, its channel group, or group + shared group)."""
         raise NotImplementedError()
+
+    def forward_output_heads(self, stacked_latent_values, tasks: Optional[Sequence[str]] = None):
+        """-> {task: x_hat}.  `tasks` (an extension, used by the selective decoder) restricts the work to a subset."""
+        heads = self.model["output_heads"]
+        sel = [(i, t) for i, t in enumerate(self.tasks) if tasks is None or t in tasks]
+        outs = self._run_heads([(lambda i=i, t=t: heads[i](self._head_input(stacked_latent_values, i, t)))
+                                for i, t in sel])
+        return dict(zip([t for _, t in sel], outs))
 
     def forward(self, batch):
         out = self.model["compressor"](self.forward_input_heads(batch))
@@ -409,6 +418,80 @@ class MultiTaskCompressor(nn.Module):
         return self.forward_output_heads(c.g_s(y_hat))
 
 
+    # ------------------------------------------------------------------ (f3) container with per-group streams
+    def _coding_groups(self):
+        """[(name, first channel, channel count)]: the rate groups as contiguous channel ranges; channels that belong
+        to no group (the Disjoint model's orphans) feed no decoder and are not coded."""
+        chan, _, names = self._rate_groups()
+        groups = []
+        for gi, name in enumerate(names):
+            idx = [c for c, g in enumerate(chan) if g == gi]
+            assert idx and idx == list(range(idx[0], idx[0] + len(idx))), "rate groups are contiguous channel ranges"
+            groups.append((name, idx[0], len(idx)))
+        return groups
+
+    def _groups_for_tasks(self, tasks: Optional[Sequence[str]]):
+        names = [g[0] for g in self._coding_groups()]
+        if tasks is None or set(names) <= {"__all__"}:
+            return names
+        unknown = [t for t in tasks if t not in self.tasks]
+        if unknown:
+            raise KeyError(f"unknown task(s) {unknown}; this model codes {list(self.tasks)}")
+        return [n for n in names if n in tasks or n == "shared"]
+
+    @staticmethod
+    def _coding_scales(y_shape, scales_hat: torch.Tensor) -> torch.Tensor:
+        """The scales the y symbols are coded against.  Shape-consistent models: scales_hat itself.  The reference's
+        256^2 geometry (y (B,M,1,1) against scales (B,M,4,4): `compress` raises there) has sixteen
+        candidate scales per symbol; the container codes each symbol against their spatial MEAN - encoder and decoder
+        derive it from the same z_hat, so the choice only affects the rate, never decodability."""
+        if tuple(scales_hat.shape[-2:]) == tuple(y_shape):
+            return scales_hat
+        if all(d == 1 for d in y_shape):
+            return scales_hat.mean(dim=(2, 3), keepdim=True)
+        raise ValueError(f"cannot code y with spatial shape {tuple(y_shape)} against scales {tuple(scales_hat.shape)}")
+
+    @torch.no_grad()
+    def compress_to_container(self, batch):
+        """Inputs -> `container.Container` (call `.to_bytes()` for the on-disk form): z once, y group by group."""
+        from .container import Container
+
+        c = self.model["compressor"]
+        y = c.g_a(self.forward_input_heads(batch))
+        z = c.h_a(torch.abs(y))
+        eb, gc = c.entropy_bottleneck, c.gaussian_conditional
+        z_strings = eb.compress(z)
+        z_hat = eb.quantize(z, "dequantize", eb._get_medians().detach().reshape(1, -1, *([1] * (z.dim() - 2))))
+        indexes = gc.build_indexes(self._coding_scales(y.shape[-2:], c.h_s(z_hat)))
+        groups = self._coding_groups()
+        y_strings = {name: gc.compress(y[:, a:a + n].contiguous(), indexes[:, a:a + n].contiguous())
+                     for name, a, n in groups}
+        kind = {"SingleTaskCompressor": 1, "MultiTaskMixedLatentCompressor": 2, "MultiTaskDisjointLatentCompressor": 3,
+                "MultiTaskSharedLatentCompressor": 4}.get(type(self).__name__, 0)
+        return Container(kind, c.M, c.N, z.shape[-2:], y.shape[-2:], groups, z_strings, y_strings)
+
+    @torch.no_grad()
+    def decompress_container(self, source, tasks: Optional[Sequence[str]] = None):
+        """Container (or its bytes) -> {task: x_hat} for `tasks` (default: all).  Only z and the channel groups those
+        tasks read are sliced out of the payload and decoded, and only their output heads run."""
+        from .container import Container
+
+        wanted = self._groups_for_tasks(tasks)
+        cont = Container.from_bytes(source, groups=wanted) if isinstance(source, (bytes, bytearray, memoryview)) else source
+        c = self.model["compressor"]
+        if (cont.M, cont.N) != (c.M, c.N):
+            raise ValueError(f"container was written by a model with M = {cont.M}, N = {cont.N}; this one has {c.M}, {c.N}")
+        eb, gc = c.entropy_bottleneck, c.gaussian_conditional
+        z_hat = eb.decompress(cont.z_strings, cont.z_shape)
+        indexes = gc.build_indexes(self._coding_scales(cont.y_shape, c.h_s(z_hat)))
+        y_hat = torch.zeros((cont.n_images, c.M) + tuple(cont.y_shape), dtype=z_hat.dtype, device=z_hat.device)
+        table = {name: (a, n) for name, a, n in cont.groups}
+        for name in wanted:
+            a, n = table[name]
+            y_hat[:, a:a + n] = gc.decompress(cont.y_strings[name], indexes[:, a:a + n].contiguous(), z_hat.dtype)
+        return self.forward_output_heads(c.g_s(y_hat), tasks=tasks)
+
+
 class MultiTaskMixedLatentCompressor(MultiTaskCompressor):
     """All tasks share all M latent channels; every output head sees the whole latent (mixed_latent.py)."""
 
@@ -431,10 +514,8 @@ class MultiTaskMixedLatentCompressor(MultiTaskCompressor):
         model["output_heads"] = self._build_heads(total, self.output_channels, is_deconv=True)
         return model
 
-    def forward_output_heads(self, stacked_latent_values):
-        heads = self.model["output_heads"]
-        outs = self._run_heads([(lambda i=i: heads[i](stacked_latent_values)) for i in range(len(self.tasks))])
-        return dict(zip(self.tasks, outs))
+    def _head_input(self, stacked_latent_values, i, task):
+        return stacked_latent_values
 
 
 class SingleTaskCompressor(MultiTaskMixedLatentCompressor):
@@ -505,11 +586,8 @@ class MultiTaskDisjointLatentCompressor(MultiTaskCompressor):
         model["output_heads"] = self._build_heads(self._head_width(), self.output_channels, is_deconv=True)
         return model
 
-    def forward_output_heads(self, stacked_latent_values):
-        heads = self.model["output_heads"]
-        outs = self._run_heads([(lambda i=i, t=t: heads[i](self._get_task_channels(stacked_latent_values, t)))
-                                for i, t in enumerate(self.tasks)])
-        return dict(zip(self.tasks, outs))
+    def _head_input(self, stacked_latent_values, i, task):
+        return self._get_task_channels(stacked_latent_values, task)
 
 
 class MultiTaskSharedLatentCompressor(MultiTaskDisjointLatentCompressor):
@@ -545,17 +623,10 @@ class MultiTaskSharedLatentCompressor(MultiTaskDisjointLatentCompressor):
             return self._shared_channels(likelihoods["y"])
         return self._get_task_channels(likelihoods["y"], task)
 
-    def forward_output_heads(self, stacked_latent_values):
+    def _head_input(self, stacked_latent_values, i, task):
         B, _, H, W = stacked_latent_values.shape
-        shared = self._shared_channels(stacked_latent_values)
-        heads = self.model["output_heads"]
-
-        def run(i, t):
-            own = self._get_task_channels(stacked_latent_values, t)
-            return heads[i](torch.stack([own, shared], dim=1).reshape((B, -1, H, W)))
-
-        outs = self._run_heads([(lambda i=i, t=t: run(i, t)) for i, t in enumerate(self.tasks)])
-        return dict(zip(self.tasks, outs))
+        own = self._get_task_channels(stacked_latent_values, task)
+        return torch.stack([own, self._shared_channels(stacked_latent_values)], dim=1).reshape((B, -1, H, W))
 
 
 def build_compressor(model_type: int, tasks: Sequence[str], latent_channels: int, conv_channels: int,
