@@ -189,6 +189,18 @@ int mmnc_gdn_backward_raw(const float *x, const float *g, int64_t B, int64_t C, 
                           const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal, int inverse,
                           int precision, float *dx, float *dbeta_raw, float *dgamma_raw, void *workspace,
                           size_t workspace_bytes, void *stream);
+/* (f1) Channels-last: the same two calls for tensors stored NHWC (torch.channels_last: element (b, c, p) at
+ * ((b HW + p) C + c)), so that a model whose convolutions run channels-last on cuDNN's tensor-core kernels does not pay
+ * NCHW <-> NHWC conversions around every GDN.  Native for C <= 4 and for 16 <= C <= 128 forward / 16 <= C <= 111
+ * backward at single-pass TF32 (auto / tf32); mmnc_gdn_nhwc_supported says whether a call would be accepted. */
+int mmnc_gdn_nhwc_supported(int64_t B, int64_t C, int64_t HW, int precision, int backward);
+int mmnc_gdn_forward_raw_nhwc(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
+                              const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal, int inverse,
+                              int precision, float *y, void *stream);
+int mmnc_gdn_backward_raw_nhwc(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
+                               const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal, int inverse,
+                               int precision, float *dx, float *dbeta_raw, float *dgamma_raw, void *workspace,
+                               size_t workspace_bytes, void *stream);
 /* NonNegativeParametrizer.forward: out = max(p, bound)^2 - pedestal, and its backward with LowerBound's
  * custom gradient (pass when p >= bound or when the incoming gradient is negative). */
 int mmnc_nonneg_reparam_forward(const float *p, int64_t n, float bound, float pedestal, float *out, void *stream);

@@ -57,6 +57,10 @@ SIGNATURES = {
     "mmnc_gdn_forward_raw": (I32, [VP, I64, I64, I64, VP, VP, F32, F32, F32, I32, I32, VP, VP]),
     "mmnc_gdn_backward_raw": (I32, [VP, VP, I64, I64, I64, VP, VP, F32, F32, F32, I32, I32, VP, VP, VP, VP,
                                     ctypes.c_size_t, VP]),
+    "mmnc_gdn_nhwc_supported": (I32, [I64, I64, I64, I32, I32]),
+    "mmnc_gdn_forward_raw_nhwc": (I32, [VP, I64, I64, I64, VP, VP, F32, F32, F32, I32, I32, VP, VP]),
+    "mmnc_gdn_backward_raw_nhwc": (I32, [VP, VP, I64, I64, I64, VP, VP, F32, F32, F32, I32, I32, VP, VP, VP, VP,
+                                         ctypes.c_size_t, VP]),
     "mmnc_nonneg_reparam_forward": (I32, [VP, I64, F32, F32, VP, VP]),
     "mmnc_nonneg_reparam_backward": (I32, [VP, VP, I64, F32, VP, VP]),
     "mmnc_argmax_sse": (I32, [VP, VP, I64, I32, I64, VP, VP, VP]),

@@ -109,6 +109,10 @@ class MultiTaskCompressor(nn.Module):
         # step metrics (mtc.py:92, 359-384, 468): the reference evaluates PSNR and MS-SSIM of every task on EVERY step.
         # Validation steps do the same here; training steps every `train_metrics_every` steps (0 = never, 1 = the
         # reference's behaviour) - MS-SSIM is ~40 filtering passes per task and is not part of the loss.
+        # (f1) run the whole network channels-last: cuDNN's tensor-core convolutions are NHWC kernels, and with NCHW
+        # tensors it converts around every one of them (~27 % of the training step's GPU time, profiles/); the GDN
+        # kernels take NHWC natively for the large layers.  Switch with use_channels_last().
+        self.channels_last = False
         self.metrics = ("psnr", "ms-ssim")
         self.train_metrics_every = 0
         self._train_steps = 0
@@ -190,7 +194,19 @@ class MultiTaskCompressor(nn.Module):
             o.record_stream(main)
         return outs
 
+    def use_channels_last(self, enabled: bool = True):
+        """Stores the convolution weights channels-last and feeds the heads channels-last inputs (same numbers)."""
+        self.channels_last = bool(enabled)
+        self.to(memory_format=torch.channels_last if enabled else torch.contiguous_format)
+        return self
+
+    def _as_model_format(self, batch):
+        if not self.channels_last:
+            return batch
+        return {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in batch.items()}
+
     def forward_input_heads(self, batch) -> torch.Tensor:
+        batch = self._as_model_format(batch)
         heads = self.model["input_heads"]
         return torch.concat(self._run_heads([(lambda i=i, t=t: heads[i](batch[t])) for i, t in enumerate(self.tasks)]),
                             dim=1)
@@ -344,6 +360,7 @@ class MultiTaskCompressor(nn.Module):
     # ------------------------------------------------------------------ steps (mtc.py:420-483)
     def _step(self, batch, is_train: bool):
         log_dir = "train" if is_train else "val"
+        batch = self._as_model_format(batch)  # once: the loss reads the inputs in the same layout as the outputs
         x_hats, likelihoods = self.forward(batch)
         loss, log_dict = self.rate_distortion_loss(batch, x_hats, likelihoods, log_dir)
         if is_train:

@@ -43,12 +43,12 @@ int gdn_simt_backward(const float *, const float *, int64_t, int64_t, int64_t, c
 // gdn_small.cu
 bool gdn_small_supported(int64_t C);
 size_t gdn_small_backward_workspace(int64_t B, int64_t C, int64_t HW);
-int gdn_small_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, cudaStream_t);
+int gdn_small_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, cudaStream_t, int nhwc = 0);
 int gdn_small_backward(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
-                       float *, void *, size_t, cudaStream_t);
+                       float *, void *, size_t, cudaStream_t, int nhwc = 0);
 // gdn_tc.cu
 bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision);
-int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, int, float *, cudaStream_t);
+int gdn_tc_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, int, float *, cudaStream_t, int nhwc = 0);
 // gdn_tc_fwd2.cu
 bool gdn_tc_forward2_supported(const float *x, const float *y, int64_t B, int64_t C, int64_t HW);
 // gdn_tc_bwd2.cu
@@ -60,7 +60,7 @@ int gdn_tc_backward2(const float *, const float *, int64_t, int64_t, int64_t, co
 bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW);
 size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW);
 int gdn_tc_backward(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
-                    float *, void *, size_t, cudaStream_t);
+                    float *, void *, size_t, cudaStream_t, int nhwc = 0);
 
 }  // namespace mmnc
 
@@ -71,8 +71,21 @@ extern "C" const char *mmnc_last_error(void) { return g_error; }
 extern "C" uint64_t mmnc_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int mmnc_device_sm_count(void) { return sm_count(); }
 
+// Channels-last (NHWC) tensors are taken natively by the streaming kernels (C <= 4) and by the tensor-core kernels with
+// per-thread row access (forward C <= 128, backward C <= 111, single-pass TF32); everything else is NCHW only and the
+// caller converts (mmnc_gdn_nhwc_supported tells which).
+static bool gdn_nhwc_ok(int64_t B, int64_t C, int64_t HW, int precision, int backward) {
+    if (gdn_small_supported(C)) return true;
+    if (!(precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32)) return false;
+    return backward ? gdn_tc_backward_supported(B, C, HW) : gdn_tc_supported(B, C, HW, MMNC_GDN_TF32);
+}
+
+extern "C" int mmnc_gdn_nhwc_supported(int64_t B, int64_t C, int64_t HW, int precision, int backward) {
+    return gdn_nhwc_ok(B, C, HW, precision, backward) ? 1 : 0;
+}
+
 static int gdn_forward_impl(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse,
-                            int precision, float *y, void *stream) {
+                            int precision, float *y, void *stream, int nhwc = 0) {
     MMNC_REQUIRE(B >= 0 && C >= 0 && HW >= 0, "gdn_forward: negative dimension");
     MMNC_REQUIRE(precision >= 0 && precision <= 3, "gdn_forward: bad precision %d", precision);
     if (B * C * HW == 0) return MMNC_OK;
@@ -80,6 +93,12 @@ static int gdn_forward_impl(const float *x, int64_t B, int64_t C, int64_t HW, co
     MMNC_REQUIRE(C <= 8192, "gdn_forward: C = %lld too large", (long long)C);
     // `precision` names the arithmetic the caller accepts.  Tensor cores are used when the shape suits the tcgen05
     // kernel in that arithmetic; everything else runs on the fp32 SIMT kernel, which is at least as accurate.
+    if (nhwc) {
+        MMNC_REQUIRE(gdn_nhwc_ok(B, C, HW, precision, 0), "gdn_forward: no channels-last kernel for C = %lld at this precision",
+                     (long long)C);
+        if (gdn_small_supported(C)) return gdn_small_forward(x, B, C, HW, prm, inverse, y, as_stream(stream), 1);
+        return gdn_tc_forward(x, B, C, HW, prm, inverse, MMNC_GDN_TF32, y, as_stream(stream), 1);
+    }
     if (gdn_small_supported(C)) return gdn_small_forward(x, B, C, HW, prm, inverse, y, as_stream(stream));  // fp32
     const int want = (precision == MMNC_GDN_AUTO) ? MMNC_GDN_TF32 : precision;
     if (want != MMNC_GDN_FP32 && gdn_tc_supported(B, C, HW, want))
@@ -103,6 +122,13 @@ extern "C" int mmnc_gdn_forward_raw(const float *x, int64_t B, int64_t C, int64_
                                     int inverse, int precision, float *y, void *stream) {
     return gdn_forward_impl(x, B, C, HW, gdn_raw(beta_raw, gamma_raw, beta_bound, gamma_bound, pedestal), inverse,
                             precision, y, stream);
+}
+
+extern "C" int mmnc_gdn_forward_raw_nhwc(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
+                                         const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal,
+                                         int inverse, int precision, float *y, void *stream) {
+    return gdn_forward_impl(x, B, C, HW, gdn_raw(beta_raw, gamma_raw, beta_bound, gamma_bound, pedestal), inverse,
+                            precision, y, stream, 1);
 }
 
 extern "C" size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int precision) {
@@ -135,7 +161,7 @@ extern "C" int mmnc_gdn_forward_variant(const float *x, const float *y, int64_t 
 
 static int gdn_backward_impl(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
                              int inverse, int precision, float *dx, float *dbeta, float *dgamma, void *workspace,
-                             size_t workspace_bytes, void *stream) {
+                             size_t workspace_bytes, void *stream, int nhwc = 0) {
     MMNC_REQUIRE(B >= 0 && C >= 0 && HW >= 0, "gdn_backward: negative dimension");
     MMNC_REQUIRE(precision >= 0 && precision <= 3, "gdn_backward: bad precision %d", precision);
     MMNC_REQUIRE(dbeta && dgamma, "gdn_backward: null pointer");
@@ -150,6 +176,15 @@ static int gdn_backward_impl(const float *x, const float *g, int64_t B, int64_t 
     MMNC_REQUIRE(C <= 8192, "gdn_backward: C = %lld too large", (long long)C);
     // single-pass TF32 on the tensor cores when the caller accepts it (auto / tf32) and the shape suits the kernel;
     // fp32 and 3xtf32 requests, small problems and unusual channel counts run the exact fp32 SIMT kernels
+    if (nhwc) {
+        MMNC_REQUIRE(gdn_nhwc_ok(B, C, HW, precision, 1), "gdn_backward: no channels-last kernel for C = %lld at this precision",
+                     (long long)C);
+        if (gdn_small_supported(C))
+            return gdn_small_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+                                      as_stream(stream), 1);
+        return gdn_tc_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+                               as_stream(stream), 1);
+    }
     if (gdn_small_supported(C))
         return gdn_small_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
                                   as_stream(stream));
@@ -179,4 +214,13 @@ extern "C" int mmnc_gdn_backward_raw(const float *x, const float *g, int64_t B, 
                                      void *stream) {
     return gdn_backward_impl(x, g, B, C, HW, gdn_raw(beta_raw, gamma_raw, beta_bound, gamma_bound, pedestal), inverse,
                              precision, dx, dbeta_raw, dgamma_raw, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mmnc_gdn_backward_raw_nhwc(const float *x, const float *g, int64_t B, int64_t C, int64_t HW,
+                                          const float *beta_raw, const float *gamma_raw, float beta_bound,
+                                          float gamma_bound, float pedestal, int inverse, int precision, float *dx,
+                                          float *dbeta_raw, float *dgamma_raw, void *workspace, size_t workspace_bytes,
+                                          void *stream) {
+    return gdn_backward_impl(x, g, B, C, HW, gdn_raw(beta_raw, gamma_raw, beta_bound, gamma_bound, pedestal), inverse,
+                             precision, dx, dbeta_raw, dgamma_raw, workspace, workspace_bytes, stream, 1);
 }

@@ -25,7 +25,9 @@ __device__ __forceinline__ void vstore(float *p, const float (&v)[V]) {
     else __stcs(p, v[0]);
 }
 
-template <int C, int V, bool kBackward>
+// kNHWC: channels-last input / output - the V pixels of a thread are C * V consecutive floats (C float4 when V = 4),
+// de-interleaved in registers.
+template <int C, int V, bool kBackward, bool kNHWC = false>
 __global__ void __launch_bounds__(GS_THREADS)
 gdn_small_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t NP, int64_t HW, const GdnParams prm,
                  int inverse, float *__restrict__ out, float *__restrict__ part) {
@@ -48,10 +50,26 @@ gdn_small_kernel(const float *__restrict__ x, const float *__restrict__ g, int64
         const int64_t b = P / HW;
         const int64_t base = b * C * HW + (P - b * HW);
         float xv[C][V], gv[C][V];
+        if constexpr (kNHWC) {
+            float tx[C][V], tg[C][V];  // flat view: element (pixel v, channel c) sits at v * C + c
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            vload<V>(x + base + c * HW, xv[c]);
-            if (kBackward) vload<V>(g + base + c * HW, gv[c]);
+            for (int k = 0; k < C; ++k) {
+                vload<V>(x + P * C + k * V, tx[k]);
+                if (kBackward) vload<V>(g + P * C + k * V, tg[k]);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    xv[c][v] = (&tx[0][0])[v * C + c];
+                    if (kBackward) gv[c][v] = (&tg[0][0])[v * C + c];
+                }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                vload<V>(x + base + c * HW, xv[c]);
+                if (kBackward) vload<V>(g + base + c * HW, gv[c]);
+            }
         }
         float res[C][V];
 #pragma unroll
@@ -89,8 +107,18 @@ gdn_small_kernel(const float *__restrict__ x, const float *__restrict__ g, int64
                 }
             }
         }
+        if constexpr (kNHWC) {
+            float to[C][V];
 #pragma unroll
-        for (int c = 0; c < C; ++c) vstore<V>(out + base + c * HW, res[c]);
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int v = 0; v < V; ++v) (&to[0][0])[v * C + c] = res[c][v];
+#pragma unroll
+            for (int k = 0; k < C; ++k) vstore<V>(out + P * C + k * V, to[k]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) vstore<V>(out + base + c * HW, res[c]);
+        }
     }
     if (kBackward) {
         __shared__ float red[GS_THREADS / 32][C * (C + 1)];
@@ -131,39 +159,45 @@ size_t gdn_small_backward_workspace(int64_t B, int64_t C, int64_t HW) {
 
 template <int C, bool kBackward>
 static int launch_small(const float *x, const float *g, int64_t NP, int64_t HW, const GdnParams &prm, int inverse,
-                        float *out, float *part, int *grid_out, cudaStream_t s) {
-    const bool vec = (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
-                                        reinterpret_cast<uintptr_t>(g)) % 16 == 0);
+                        float *out, float *part, int *grid_out, cudaStream_t s, int nhwc) {
+    const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(g)) % 16 == 0);
+    // NCHW: four pixels of one image plane; NHWC: four pixels = 4 C consecutive floats anywhere in the tensor
+    const bool vec = al && (nhwc ? (NP % 4 == 0) : (HW % 4 == 0));
     const int grid = small_grid(NP, vec ? 4 : 1);
     *grid_out = grid;
-    if (vec) gdn_small_kernel<C, 4, kBackward><<<grid, GS_THREADS, 0, s>>>(x, g, NP, HW, prm, inverse, out, part);
-    else gdn_small_kernel<C, 1, kBackward><<<grid, GS_THREADS, 0, s>>>(x, g, NP, HW, prm, inverse, out, part);
+    if (nhwc && C > 1) {  // C = 1: both memory formats are the same bytes
+        if (vec) gdn_small_kernel<C, 4, kBackward, true><<<grid, GS_THREADS, 0, s>>>(x, g, NP, HW, prm, inverse, out, part);
+        else gdn_small_kernel<C, 1, kBackward, true><<<grid, GS_THREADS, 0, s>>>(x, g, NP, HW, prm, inverse, out, part);
+    } else {
+        if (vec) gdn_small_kernel<C, 4, kBackward><<<grid, GS_THREADS, 0, s>>>(x, g, NP, HW, prm, inverse, out, part);
+        else gdn_small_kernel<C, 1, kBackward><<<grid, GS_THREADS, 0, s>>>(x, g, NP, HW, prm, inverse, out, part);
+    }
     return after_launch(kBackward ? "gdn_small_kernel<bwd>" : "gdn_small_kernel<fwd>");
 }
 
 int gdn_small_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, float *y,
-                      cudaStream_t s) {
+                      cudaStream_t s, int nhwc) {
     int grid;
     switch (C) {
-        case 1: return launch_small<1, false>(x, nullptr, B * HW, HW, prm, inverse, y, nullptr, &grid, s);
-        case 2: return launch_small<2, false>(x, nullptr, B * HW, HW, prm, inverse, y, nullptr, &grid, s);
-        case 3: return launch_small<3, false>(x, nullptr, B * HW, HW, prm, inverse, y, nullptr, &grid, s);
-        case 4: return launch_small<4, false>(x, nullptr, B * HW, HW, prm, inverse, y, nullptr, &grid, s);
+        case 1: return launch_small<1, false>(x, nullptr, B * HW, HW, prm, inverse, y, nullptr, &grid, s, nhwc);
+        case 2: return launch_small<2, false>(x, nullptr, B * HW, HW, prm, inverse, y, nullptr, &grid, s, nhwc);
+        case 3: return launch_small<3, false>(x, nullptr, B * HW, HW, prm, inverse, y, nullptr, &grid, s, nhwc);
+        case 4: return launch_small<4, false>(x, nullptr, B * HW, HW, prm, inverse, y, nullptr, &grid, s, nhwc);
         default: set_error("gdn_small_forward: C out of range"); return MMNC_ERR_UNSUPPORTED;
     }
 }
 
 int gdn_small_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
                        int inverse, float *dx, float *dbeta, float *dgamma, void *workspace, size_t workspace_bytes,
-                       cudaStream_t s) {
+                       cudaStream_t s, int nhwc) {
     MMNC_REQUIRE(workspace_bytes >= gdn_small_backward_workspace(B, C, HW), "gdn_backward: workspace too small");
     float *part = static_cast<float *>(workspace);
     int grid = 0, rc;
     switch (C) {
-        case 1: rc = launch_small<1, true>(x, g, B * HW, HW, prm, inverse, dx, part, &grid, s); break;
-        case 2: rc = launch_small<2, true>(x, g, B * HW, HW, prm, inverse, dx, part, &grid, s); break;
-        case 3: rc = launch_small<3, true>(x, g, B * HW, HW, prm, inverse, dx, part, &grid, s); break;
-        case 4: rc = launch_small<4, true>(x, g, B * HW, HW, prm, inverse, dx, part, &grid, s); break;
+        case 1: rc = launch_small<1, true>(x, g, B * HW, HW, prm, inverse, dx, part, &grid, s, nhwc); break;
+        case 2: rc = launch_small<2, true>(x, g, B * HW, HW, prm, inverse, dx, part, &grid, s, nhwc); break;
+        case 3: rc = launch_small<3, true>(x, g, B * HW, HW, prm, inverse, dx, part, &grid, s, nhwc); break;
+        case 4: rc = launch_small<4, true>(x, g, B * HW, HW, prm, inverse, dx, part, &grid, s, nhwc); break;
         default: set_error("gdn_small_backward: C out of range"); return MMNC_ERR_UNSUPPORTED;
     }
     if (rc) return rc;

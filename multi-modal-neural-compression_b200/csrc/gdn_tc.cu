@@ -19,6 +19,7 @@
 #include "gdn_params.cuh"
 #include "tc_ptx.cuh"
 #include "tma_host.cuh"
+#include "gdn_nhwc.cuh"
 
 namespace mmnc {
 
@@ -38,11 +39,11 @@ struct Geometry {
 // loaded from HBM once, squared into the A operand, and reused by the epilogue — 8 B/element of traffic, the
 // algorithmic minimum.  kBetaInMma: when C is not a multiple of 8 the K padding is free, so one padded A column
 // is the constant 1 and the matching B row holds beta: the accumulator comes back as beta + sum gamma x^2.
-template <bool k3x, int KP8, bool kBetaInMma, bool kFull>
+template <bool k3x, int KP8, bool kBetaInMma, bool kFull, bool kNHWC = false>
 __device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float *__restrict__ yb, int64_t HW, int C,
                                             bool inverse, bool valid, const float *beta_s, uint32_t tmem_base, uint32_t lane_base,
                                             uint32_t d_col, uint64_t desc_hi, uint64_t desc_lo, uint32_t idesc,
-                                            uint64_t *mbar, uint32_t parity) {
+                                            uint64_t *mbar, uint32_t parity, int vec = 1) {
     using namespace tc;
     constexpr int Kp = KP8 * 8;
     constexpr int NP16 = (KP8 + 1) / 2;  // Np / 16
@@ -51,11 +52,15 @@ __device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float 
     // Padded channels (c >= C) re-read the last real channel: their B rows are zero, so any finite value works.
     const uint32_t sb = (uint32_t)HW * 4u;  // channel stride in bytes
     float xv[Kp];
+    if constexpr (kNHWC) {
+        nhwc_load_row<Kp>(xb, C, vec, kFull || valid, xv);  // xb = this pixel's row
+    } else {
 #pragma unroll
-    for (int c = 0; c < Kp; ++c) {
-        const int cc = (c < Kp - 8) ? c : ((c < C) ? c : C - 1);
-        xv[c] = (kFull || valid) ? __ldcs(chan_ptr(xb, sb, cc)) : 0.f;
-        if ((c & 7) == 7) asm volatile("" ::: "memory");  // keep address arithmetic next to its load (register pressure)
+        for (int c = 0; c < Kp; ++c) {
+            const int cc = (c < Kp - 8) ? c : ((c < C) ? c : C - 1);
+            xv[c] = (kFull || valid) ? __ldcs(chan_ptr(xb, sb, cc)) : 0.f;
+            if ((c & 7) == 7) asm volatile("" ::: "memory");  // keep address arithmetic next to its load (register pressure)
+        }
     }
     // ---- A operand: x^2 -> tf32 -> TMEM (lane = pixel, column = channel)
 #pragma unroll
@@ -96,17 +101,25 @@ __device__ __forceinline__ void gdn_tc_tile(const float *__restrict__ xb, float 
         uint32_t r[16];
         tmem_ld16(lane_base + d_col + q * 16, r);
         tmem_ld_wait();
+        float o16[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int i = q * 16 + j;
+            o16[j] = 0.f;
             if (i < Kp) {
                 float n = __uint_as_float(r[j]);
                 if (!kBetaInMma) n += beta_s[i];
                 const float rs = fast_rsqrt(n);
                 const float out = xv[i] * (inverse ? n * rs : rs);
-                const bool ok = (kFull || valid) && (i < Kp - 8 || i < C);
-                if (ok) __stcs(chan_ptr(yb, sb, i), out);
+                o16[j] = out;
+                if constexpr (!kNHWC) {
+                    const bool ok = (kFull || valid) && (i < Kp - 8 || i < C);
+                    if (ok) __stcs(chan_ptr(yb, sb, i), out);
+                }
             }
+        }
+        if constexpr (kNHWC) {
+            if (kFull || valid) nhwc_store_block<16>(yb, q * 16, C, vec, o16);
         }
     }
     fence_before();
@@ -121,11 +134,11 @@ constexpr int tc_fwd_ctas() {
     return need <= 128 ? 4 : (need <= 256 ? 2 : 1);
 }
 
-template <bool k3x, int KP8, bool kBetaInMma>
+template <bool k3x, int KP8, bool kBetaInMma, bool kNHWC = false>
 __global__ void __launch_bounds__(tc::TILE_M, tc_fwd_ctas<k3x, KP8>())
 gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const GdnParams prm, int inverse,
                       float *__restrict__ y, int C, int Np, int d_col_i,
-                      uint32_t tmem_cols, uint32_t b_bytes) {
+                      uint32_t tmem_cols, uint32_t b_bytes, int vec) {
     using namespace tc;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t mbar;
@@ -189,13 +202,14 @@ gdn_tc_forward_kernel(const float *__restrict__ x, int64_t NP, int64_t HW, const
         const bool full = (tile + 1) * TILE_M <= NP;
         const bool valid = P < NP;
         const int64_t b = valid ? P / HW : 0;
-        const int64_t base = b * C * HW + (valid ? P - b * HW : 0);
+        // NCHW: (image, pixel) -> first channel of that pixel; NHWC: the pixel's row of C channels
+        const int64_t base = kNHWC ? (valid ? P * C : 0) : (b * C * HW + (valid ? P - b * HW : 0));
         if (full)
-            gdn_tc_tile<k3x, KP8, kBetaInMma, true>(x + base, y + base, HW, C, inverse != 0, true, beta_s, tmem_base, lane_base,
-                                                              d_col, desc_hi, desc_lo, idesc, &mbar, parity);
+            gdn_tc_tile<k3x, KP8, kBetaInMma, true, kNHWC>(x + base, y + base, HW, C, inverse != 0, true, beta_s, tmem_base,
+                                                           lane_base, d_col, desc_hi, desc_lo, idesc, &mbar, parity, vec);
         else
-            gdn_tc_tile<k3x, KP8, kBetaInMma, false>(x + base, y + base, HW, C, inverse != 0, valid, beta_s, tmem_base,
-                                                               lane_base, d_col, desc_hi, desc_lo, idesc, &mbar, parity);
+            gdn_tc_tile<k3x, KP8, kBetaInMma, false, kNHWC>(x + base, y + base, HW, C, inverse != 0, valid, beta_s, tmem_base,
+                                                            lane_base, d_col, desc_hi, desc_lo, idesc, &mbar, parity, vec);
         parity ^= 1;
     }
     __syncthreads();
@@ -230,11 +244,19 @@ bool gdn_tc_supported(int64_t B, int64_t C, int64_t HW, int precision) {
     return tc_geometry(C, precision == MMNC_GDN_3XTF32, &g) && C >= 16 && B * HW >= 128 && HW < (1 << 24);
 }
 
+// vector width of a channels-last row access: the row stride is C floats, so C and the base must allow it
+int gdn_nhwc_vec(const void *a, const void *b, const void *c, int64_t C) {
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c);
+    if (C % 4 == 0 && (bits & 15) == 0) return 4;
+    if (C % 2 == 0 && (bits & 7) == 0) return 2;
+    return 1;
+}
+
 int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, int precision,
-                   float *y, cudaStream_t s) {
+                   float *y, cudaStream_t s, int nhwc) {
     tc::Geometry g;
     const bool k3x = (precision == MMNC_GDN_3XTF32);
-    if (!k3x && gdn_tc_forward2_supported(x, y, B, C, HW)) return gdn_tc_forward2(x, B, C, HW, prm, inverse, y, s);
+    if (!nhwc && !k3x && gdn_tc_forward2_supported(x, y, B, C, HW)) return gdn_tc_forward2(x, B, C, HW, prm, inverse, y, s);
     if (!tc_geometry(C, k3x, &g)) {
         set_error("gdn_tc_forward: C = %lld not supported by the tensor-core path", (long long)C);
         return MMNC_ERR_UNSUPPORTED;
@@ -254,12 +276,17 @@ int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnPa
         return MMNC_ERR_UNSUPPORTED;
     }
     using Kernel = void (*)(const float *, int64_t, int64_t, const GdnParams, int, float *, int, int, int, uint32_t,
-                            uint32_t);
+                            uint32_t, int);
     Kernel kernel = nullptr;
     const bool beta_in_mma = (C % 8) != 0;
+    if (nhwc && k3x) {
+        set_error("gdn_tc_forward: the channels-last kernels are single-pass TF32 only");
+        return MMNC_ERR_UNSUPPORTED;
+    }
 #define MMNC_TC_CASE(N)                                                                                        \
     case N:                                                                                                    \
-        if (k3x) kernel = beta_in_mma ? (Kernel)gdn_tc_forward_kernel<true, N, true> : (Kernel)gdn_tc_forward_kernel<true, N, false>;   \
+        if (nhwc) kernel = beta_in_mma ? (Kernel)gdn_tc_forward_kernel<false, N, true, true> : (Kernel)gdn_tc_forward_kernel<false, N, false, true>; \
+        else if (k3x) kernel = beta_in_mma ? (Kernel)gdn_tc_forward_kernel<true, N, true> : (Kernel)gdn_tc_forward_kernel<true, N, false>;   \
         else     kernel = beta_in_mma ? (Kernel)gdn_tc_forward_kernel<false, N, true> : (Kernel)gdn_tc_forward_kernel<false, N, false>; \
         break;
     switch (g.Kp / 8) {
@@ -279,8 +306,8 @@ int gdn_tc_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnPa
     int64_t grid = (int64_t)sm_count() * (max_ctas < 4 ? max_ctas : 4);
     if (grid > tiles) grid = tiles;
     kernel<<<(unsigned)grid, tc::TILE_M, smem, s>>>(x, NP, HW, prm, inverse, y, g.C, g.Np, g.d_col, g.tmem_cols,
-                                                    (uint32_t)g.b_bytes);
-    return after_launch(k3x ? "gdn_tc_forward_kernel<3xtf32>" : "gdn_tc_forward_kernel<tf32>");
+                                                    (uint32_t)g.b_bytes, nhwc ? gdn_nhwc_vec(x, y, nullptr, C) : 1);
+    return after_launch(k3x ? "gdn_tc_forward_kernel<3xtf32>" : (nhwc ? "gdn_tc_forward_kernel<tf32, nhwc>" : "gdn_tc_forward_kernel<tf32>"));
 }
 
 }  // namespace mmnc

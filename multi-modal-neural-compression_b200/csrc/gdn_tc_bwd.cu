@@ -22,6 +22,7 @@
 #include "gdn_params.cuh"
 #include "tc_ptx.cuh"
 #include "tma_host.cuh"
+#include "gdn_nhwc.cuh"
 
 namespace mmnc {
 
@@ -59,20 +60,20 @@ __device__ __forceinline__ void v1_ss_chain(uint32_t d3, uint32_t a_lo, uint32_t
 // parameters so that every channel index below is a compile-time constant: only the last 16 padded channels of
 // HALF 1 keep run-time checks against C, everything else is straight-line code with immediate offsets.
 struct TileCtx {
-    int HW, C, pix, R8;
+    int HW, C, pix, R8, vec;
     uint32_t tmem_base, lane_base, idesc;
     uint8_t *ubuf, *x2buf;
     uint64_t desc_b1, desc_b2, desc_a3, desc_b3;
     uint64_t *mbar;
 };
 
-template <int KH8, int HALF, bool kInverse, bool kFull>
+template <int KH8, int HALF, bool kInverse, bool kFull, bool kNHWC = false>
 __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ xb, const float *__restrict__ gb,
                                                 float *__restrict__ dxb, int HW, int C, bool valid, int pix,
                                                 uint32_t tmem_base, uint32_t lane_base, uint8_t *ubuf,
                                                 uint8_t *x2buf, int R8, uint64_t desc_b1, uint64_t desc_b2,
                                                 uint64_t desc_a3, uint64_t desc_b3, uint32_t idesc, uint64_t *mbar,
-                                                uint32_t &parity, bool first_tile) {
+                                                uint32_t &parity, bool first_tile, int vec = 1) {
     using namespace tc;
     using namespace tcb;
     constexpr int KH = KH8 * 8;        // channels handled by this thread
@@ -97,15 +98,21 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
 
     // ---- loads: this thread's channels of x and g, all in flight (32-bit element offsets from a per-pixel base)
     float xv[KH], gv[KH];
+    if constexpr (kNHWC) {
+        // xb / gb / dxb = this pixel's row; the thread owns channels [c_begin, c_begin + KH) of it (0 beyond C)
+        nhwc_load_row<KH>(xb + c_begin, C - c_begin, vec, ok, xv);
+        nhwc_load_row<KH>(gb + c_begin, C - c_begin, vec, ok, gv);
+    } else {
 #pragma unroll
-    for (int j = 0; j < KH; ++j) {
-        const int c = c_begin + j;
-        const int cc = (c < SAFE) ? c : ((c < C) ? c : C - 1);  // padded channels re-read a real one (weights are 0)
-        xv[j] = ok ? __ldcs(chan_ptr(xb, sb, cc)) : 0.f;
-        gv[j] = ok ? __ldcs(chan_ptr(gb, sb, cc)) : 0.f;
-        // compile-time fence every 4 channels: keeps the address arithmetic next to its load instead of letting the
-        // scheduler materialise all 2 KH 64-bit addresses first (the loads still issue back to back)
-        if ((j & 3) == 3) asm volatile("" ::: "memory");
+        for (int j = 0; j < KH; ++j) {
+            const int c = c_begin + j;
+            const int cc = (c < SAFE) ? c : ((c < C) ? c : C - 1);  // padded channels re-read a real one (weights are 0)
+            xv[j] = ok ? __ldcs(chan_ptr(xb, sb, cc)) : 0.f;
+            gv[j] = ok ? __ldcs(chan_ptr(gb, sb, cc)) : 0.f;
+            // compile-time fence every 4 channels: keeps the address arithmetic next to its load instead of letting the
+            // scheduler materialise all 2 KH 64-bit addresses first (the loads still issue back to back)
+            if ((j & 3) == 3) asm volatile("" ::: "memory");
+        }
     }
     // ---- x^2 -> A (TMEM) and -> x2buf (smem, K = pixel); padded channel C is the constant 1
 #pragma unroll
@@ -179,11 +186,18 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
         uint32_t r[8];
         tmem_ld8(lane_base + d_col + c_begin + j0, r);
         tmem_ld_wait();
+        float o8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = c_begin + j0 + j;
             const float out = fmaf(2.f * xv[j0 + j], __uint_as_float(r[j]), gv[j0 + j]);
-            if (ok && (c < SAFE || c < C)) __stcs(chan_ptr(dxb, sb, c), out);
+            o8[j] = out;
+            if constexpr (!kNHWC) {
+                if (ok && (c < SAFE || c < C)) __stcs(chan_ptr(dxb, sb, c), out);
+            }
+        }
+        if constexpr (kNHWC) {
+            if (ok) nhwc_store_block<8>(dxb, c_begin + j0, C, vec, o8);
         }
     }
     fence_before();
@@ -193,15 +207,15 @@ __device__ __forceinline__ void gdn_tc_bwd_tile_body(const float *__restrict__ x
 
 // the rare partial tile (last tile of the tensor) takes the predicated body out of line so that it does not
 // weigh on the register allocation of the steady-state loop
-template <int KH8, int HALF, bool kInverse>
+template <int KH8, int HALF, bool kInverse, bool kNHWC>
 __device__ __noinline__ void gdn_tc_bwd_tile_partial(const float *xb, const float *gb, float *dxb, bool valid,
                                                      const TileCtx &t, uint32_t &parity, bool first) {
-    gdn_tc_bwd_tile_body<KH8, HALF, kInverse, false>(xb, gb, dxb, t.HW, t.C, valid, t.pix, t.tmem_base, t.lane_base,
-                                                     t.ubuf, t.x2buf, t.R8, t.desc_b1, t.desc_b2, t.desc_a3, t.desc_b3,
-                                                     t.idesc, t.mbar, parity, first);
+    gdn_tc_bwd_tile_body<KH8, HALF, kInverse, false, kNHWC>(xb, gb, dxb, t.HW, t.C, valid, t.pix, t.tmem_base, t.lane_base,
+                                                            t.ubuf, t.x2buf, t.R8, t.desc_b1, t.desc_b2, t.desc_a3,
+                                                            t.desc_b3, t.idesc, t.mbar, parity, first, t.vec);
 }
 
-template <int KH8, int HALF, bool kInverse>
+template <int KH8, int HALF, bool kInverse, bool kNHWC>
 __device__ __forceinline__ bool gdn_tc_bwd_loop(const float *__restrict__ x, const float *__restrict__ g,
                                                 float *__restrict__ dx, int64_t NP, int64_t HW, const TileCtx &t) {
     using namespace tcb;
@@ -211,24 +225,25 @@ __device__ __forceinline__ bool gdn_tc_bwd_loop(const float *__restrict__ x, con
         const int64_t Pix = tile * TILE + t.pix;
         const bool valid = Pix < NP;
         const int64_t b = valid ? Pix / HW : 0;
-        const int64_t base = b * t.C * HW + (valid ? Pix - b * HW : 0);
+        // NCHW: first channel of the pixel inside its image; NHWC: the pixel's row
+        const int64_t base = kNHWC ? (valid ? Pix * t.C : 0) : (b * t.C * HW + (valid ? Pix - b * HW : 0));
         if ((tile + 1) * TILE <= NP)
-            gdn_tc_bwd_tile_body<KH8, HALF, kInverse, true>(x + base, g + base, dx + base, t.HW, t.C, true, t.pix,
-                                                            t.tmem_base, t.lane_base, t.ubuf, t.x2buf, t.R8, t.desc_b1,
-                                                            t.desc_b2, t.desc_a3, t.desc_b3, t.idesc, t.mbar, parity,
-                                                            first);
+            gdn_tc_bwd_tile_body<KH8, HALF, kInverse, true, kNHWC>(x + base, g + base, dx + base, t.HW, t.C, true, t.pix,
+                                                                   t.tmem_base, t.lane_base, t.ubuf, t.x2buf, t.R8,
+                                                                   t.desc_b1, t.desc_b2, t.desc_a3, t.desc_b3, t.idesc,
+                                                                   t.mbar, parity, first, t.vec);
         else
-            gdn_tc_bwd_tile_partial<KH8, HALF, kInverse>(x + base, g + base, dx + base, valid, t, parity, first);
+            gdn_tc_bwd_tile_partial<KH8, HALF, kInverse, kNHWC>(x + base, g + base, dx + base, valid, t, parity, first);
         first = false;
     }
     return first;
 }
 
-template <int KH8, bool kInverse>
+template <int KH8, bool kInverse, bool kNHWC = false>
 __global__ void __launch_bounds__(tcb::THREADS, (KH8 <= 4) ? 2 : 1)
 gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g, int64_t NP, int64_t HW,
                        const GdnParams prm,
-                       float *__restrict__ dx, float *__restrict__ part, int C, uint32_t tmem_cols) {
+                       float *__restrict__ dx, float *__restrict__ part, int C, uint32_t tmem_cols, int vec) {
     using namespace tc;
     using namespace tcb;
     constexpr int P = KH8 * 16;
@@ -303,14 +318,14 @@ gdn_tc_backward_kernel(const float *__restrict__ x, const float *__restrict__ g,
     const uint32_t idesc = make_idesc_ex(P, false, false);
     TileCtx ctx;
     ctx.HW = (int)HW;  // channel stride in elements (< 2^31; per-pixel bases stay 64-bit)
-    ctx.C = C; ctx.pix = pix; ctx.R8 = R8;
+    ctx.C = C; ctx.pix = pix; ctx.R8 = R8; ctx.vec = vec;
     ctx.tmem_base = tmem_base; ctx.lane_base = lane_base; ctx.idesc = idesc;
     ctx.ubuf = ubuf; ctx.x2buf = x2buf;
     ctx.desc_b1 = desc_b1; ctx.desc_b2 = desc_b2; ctx.desc_a3 = desc_a3; ctx.desc_b3 = desc_b3;
     ctx.mbar = &mbar;
     // the two warpgroups run the same tile sequence in lock step, each on its half of the channels
-    const bool first = (half == 0) ? gdn_tc_bwd_loop<KH8, 0, kInverse>(x, g, dx, NP, HW, ctx)
-                                   : gdn_tc_bwd_loop<KH8, 1, kInverse>(x, g, dx, NP, HW, ctx);
+    const bool first = (half == 0) ? gdn_tc_bwd_loop<KH8, 0, kInverse, kNHWC>(x, g, dx, NP, HW, ctx)
+                                   : gdn_tc_bwd_loop<KH8, 1, kInverse, kNHWC>(x, g, dx, NP, HW, ctx);
     // ---- this CTA's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
     float *dst = part + (int64_t)blockIdx.x * C * (C + 1);
     if (!first && half == 0) {
@@ -393,8 +408,8 @@ size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW) {
 
 int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, const GdnParams &prm,
                     int inverse, float *dx, float *dbeta, float *dgamma, void *workspace, size_t workspace_bytes,
-                    cudaStream_t s) {
-    if (gdn_tc_backward2_supported(x, g, B, C, HW))
+                    cudaStream_t s, int nhwc) {
+    if (!nhwc && gdn_tc_backward2_supported(x, g, B, C, HW))
         return gdn_tc_backward2(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes, s);
     int P;
     uint32_t cols;
@@ -411,9 +426,13 @@ int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_
     const size_t min_smem = (227 * 1024) / (size_t)(max_ctas + 1) + 1;
     if (smem < min_smem) smem = min_smem;
     using Kernel = void (*)(const float *, const float *, int64_t, int64_t, const GdnParams, float *, float *, int,
-                            uint32_t);
+                            uint32_t, int);
     Kernel kernel = nullptr;
-#define MMNC_CASE(N) case N: kernel = inverse ? (Kernel)gdn_tc_backward_kernel<N, true> : (Kernel)gdn_tc_backward_kernel<N, false>; break;
+#define MMNC_CASE(N)                                                                                                          \
+    case N:                                                                                                                   \
+        if (nhwc) kernel = inverse ? (Kernel)gdn_tc_backward_kernel<N, true, true> : (Kernel)gdn_tc_backward_kernel<N, false, true>; \
+        else kernel = inverse ? (Kernel)gdn_tc_backward_kernel<N, true> : (Kernel)gdn_tc_backward_kernel<N, false>;            \
+        break;
     switch (P / 16) {
         MMNC_CASE(2) MMNC_CASE(3) MMNC_CASE(4) MMNC_CASE(5) MMNC_CASE(6) MMNC_CASE(7)
         default: break;
@@ -427,8 +446,9 @@ int gdn_tc_backward(const float *x, const float *g, int64_t B, int64_t C, int64_
     // only, and the second co-resident CTA (the whole point of the TMEM budget) never lands
     if (int rc = tmah::ensure_dynamic_smem(kernel, smem, true)) return rc;
     float *part = static_cast<float *>(workspace);
-    kernel<<<(unsigned)grid, tcb::THREADS, smem, s>>>(x, g, NP, HW, prm, dx, part, (int)C, cols);
-    if (int rc = after_launch("gdn_tc_backward_kernel")) return rc;
+    kernel<<<(unsigned)grid, tcb::THREADS, smem, s>>>(x, g, NP, HW, prm, dx, part, (int)C, cols,
+                                                      nhwc ? gdn_nhwc_vec(x, g, dx, C) : 1);
+    if (int rc = after_launch(nhwc ? "gdn_tc_backward_kernel<nhwc>" : "gdn_tc_backward_kernel")) return rc;
     return gdn_reduce_partials(part, grid, (int)C, prm, dgamma, dbeta, s);
 }
 

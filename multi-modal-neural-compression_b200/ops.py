@@ -377,7 +377,10 @@ class _DistortionFn(torch.autograd.Function):
         _need_cuda(x_hat, x)
         if x_hat.shape != x.shape:
             raise ValueError(f"shape mismatch {tuple(x_hat.shape)} vs {tuple(x.shape)}")
-        a, b = _f32c(x_hat), _f32c(x)
+        if (x_hat.stride() == x.stride() and x_hat.dtype == x.dtype == torch.float32 and _is_channels_last(x_hat)):
+            a, b = x_hat, x  # an element-wise sum does not care about the order: both channels-last, no conversion
+        else:
+            a, b = _f32c(x_hat), _f32c(x)
         out = torch.zeros((), dtype=torch.float32, device=a.device)
         _lib.check(_lib.lib().mmnc_distortion_forward(_p(a), _p(b), a.numel(), kind, scale, _p(out), _stream()))
         ctx.save_for_backward(a, b)
@@ -490,36 +493,67 @@ class _GDNFn(torch.autograd.Function):
         return dx, dbeta, dgamma, None, None
 
 
+def _is_channels_last(x: Tensor) -> bool:
+    """Stored NHWC and NOT also NCHW-contiguous (C = 1 or 1 x 1 images are the same bytes either way)."""
+    return x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+
+
 class _GDNRawFn(torch.autograd.Function):
     """GDN on the raw `beta` / `gamma` parameters: the re-parametrisation and its LowerBound gradient are fused
-    into the contraction kernels (1 launch forward, 2 backward)."""
+    into the contraction kernels (1 launch forward, 2 backward).
+
+    Memory format: a channels-last (NHWC) input is processed in place where a channels-last kernel exists
+    (`mmnc_gdn_nhwc_supported`) and the output keeps the input's format either way, so a model that runs its
+    convolutions channels-last never converts around a GDN site of the large layers."""
 
     @staticmethod
     def forward(ctx, x, beta, gamma, beta_bound, gamma_bound, pedestal, inverse, precision):
         _need_cuda(x, beta, gamma)
-        x, beta, gamma = _f32c(x), _f32c(beta), _f32c(gamma)
+        if x.dtype != torch.float32:
+            raise TypeError(f"mmnc_b200: float32 expected, got {x.dtype}")
+        beta, gamma = _f32c(beta), _f32c(gamma)
         B, C, HW = _bcs(x)
         if beta.numel() != C or gamma.shape != (C, C):
             raise ValueError(f"GDN parameters do not match {C} channels")
-        y = torch.empty_like(x)
-        _lib.check(_lib.lib().mmnc_gdn_forward_raw(_p(x), B, C, HW, _p(beta), _p(gamma), beta_bound, gamma_bound,
+        L = _lib.lib()
+        cl = _is_channels_last(x)
+        native = cl and bool(L.mmnc_gdn_nhwc_supported(B, C, HW, precision, 0))
+        if native:
+            y = torch.empty_like(x)  # preserves the channels-last strides
+            _lib.check(L.mmnc_gdn_forward_raw_nhwc(_p(x), B, C, HW, _p(beta), _p(gamma), beta_bound, gamma_bound,
                                                    pedestal, int(inverse), precision, _p(y), _stream()))
+        else:
+            x = x.contiguous()
+            y = torch.empty_like(x)
+            _lib.check(L.mmnc_gdn_forward_raw(_p(x), B, C, HW, _p(beta), _p(gamma), beta_bound, gamma_bound, pedestal,
+                                              int(inverse), precision, _p(y), _stream()))
+            if cl:
+                y = y.contiguous(memory_format=torch.channels_last)
         ctx.save_for_backward(x, beta, gamma)
-        ctx.cfg = (B, C, HW, int(inverse), precision, beta_bound, gamma_bound, pedestal)
+        ctx.cfg = (B, C, HW, int(inverse), precision, beta_bound, gamma_bound, pedestal, cl, native)
         return y
 
     @staticmethod
     def backward(ctx, g):
         x, beta, gamma = ctx.saved_tensors
-        B, C, HW, inverse, precision, bb, gb, ped = ctx.cfg
+        B, C, HW, inverse, precision, bb, gb, ped, cl, native = ctx.cfg
+        L = _lib.lib()
+        dbeta, dgamma = torch.empty_like(beta), torch.empty_like(gamma)
+        nbytes = int(L.mmnc_gdn_backward_workspace_bytes(B, C, HW, precision))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        if native and bool(L.mmnc_gdn_nhwc_supported(B, C, HW, precision, 1)):
+            g = g.contiguous(memory_format=torch.channels_last)
+            dx = torch.empty_like(x)
+            _lib.check(L.mmnc_gdn_backward_raw_nhwc(_p(x), _p(g), B, C, HW, _p(beta), _p(gamma), bb, gb, ped, inverse,
+                                                    precision, _p(dx), _p(dbeta), _p(dgamma), _p(ws), nbytes, _stream()))
+            return dx, dbeta, dgamma, None, None, None, None, None
+        x = x.contiguous()  # no-op unless the forward ran channels-last natively and the backward cannot
         g = _f32c(g)
         dx = torch.empty_like(x)
-        dbeta, dgamma = torch.empty_like(beta), torch.empty_like(gamma)
-        nbytes = int(_lib.lib().mmnc_gdn_backward_workspace_bytes(B, C, HW, precision))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        _lib.check(_lib.lib().mmnc_gdn_backward_raw(_p(x), _p(g), B, C, HW, _p(beta), _p(gamma), bb, gb, ped, inverse,
-                                                    precision, _p(dx), _p(dbeta), _p(dgamma), _p(ws), nbytes,
-                                                    _stream()))
+        _lib.check(L.mmnc_gdn_backward_raw(_p(x), _p(g), B, C, HW, _p(beta), _p(gamma), bb, gb, ped, inverse, precision,
+                                           _p(dx), _p(dbeta), _p(dgamma), _p(ws), nbytes, _stream()))
+        if cl:
+            dx = dx.contiguous(memory_format=torch.channels_last)
         return dx, dbeta, dgamma, None, None, None, None, None
 
 

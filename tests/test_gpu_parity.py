@@ -849,3 +849,76 @@ def test_launch_counter_moves():
     before = mm.launch_count()
     mm.GDN(4).to(DEV)(torch.randn(1, 4, 8, 8, device=DEV))
     assert mm.launch_count() == before + 1  # re-parametrisation fused into the contraction
+
+
+# ------------------------------------------------------------------------------------------------ (f1) channels-last
+@pytest.mark.parametrize("shape", [(4, 50, 64, 64), (2, 100, 32, 32), (3, 64, 16, 16), (2, 3, 64, 64), (5, 33, 8, 8),
+                                   (2, 111, 16, 16), (2, 128, 32, 32), (1, 17, 64, 64), (2, 20, 30, 31), (3, 3, 5, 7),
+                                   (2, 300, 4, 4), (3, 1, 16, 16)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_gdn_channels_last_matches_oracle(shape, inverse):
+    """NHWC tensors through GDN (native kernels where they exist - C <= 4 streaming, 16 <= C <= 128 tensor cores with
+    row access, vector widths 4 / 2 / 1 - and converted otherwise): output and input gradient keep the channels-last
+    format and agree with the float64 oracle at the TF32 bars (1e-3 forward, 2e-3 of the largest entry backward)."""
+    torch.manual_seed(31)
+    C = shape[1]
+    ours, ref = _pair_gdn(C, inverse, precision="auto")
+    refd = R.GDN(C, inverse=inverse).double()
+    refd.load_state_dict({k: v.double() for k, v in ref.state_dict().items()})
+    x, g = torch.randn(*shape), torch.randn(*shape)
+    cl = torch.channels_last
+    xd = x.to(DEV).contiguous(memory_format=cl).requires_grad_(True)
+    y = ours(xd)
+    y.backward(g.to(DEV).contiguous(memory_format=cl))
+    x64 = x.double().requires_grad_(True)
+    y64 = refd(x64)
+    y64.backward(g.double())
+    assert y.shape == x.shape and y.is_contiguous(memory_format=cl) and xd.grad.is_contiguous(memory_format=cl)
+
+    def close(a, b, tol):
+        return ((a.detach().cpu().double() - b.detach()).abs().max() / b.detach().abs().max()).item() <= tol
+
+    assert close(y, y64, 1e-3)
+    assert close(xd.grad, x64.grad, 2e-3) and close(ours.beta.grad, refd.beta.grad, 2e-3)
+    assert close(ours.gamma.grad, refd.gamma.grad, 2e-3)
+    # and the NCHW path on the same numbers gives the same result to TF32 accuracy
+    xn = x.to(DEV).requires_grad_(True)
+    yn = ours(xn)
+    assert yn.is_contiguous() and torch.allclose(yn, y.contiguous(), rtol=2e-3, atol=2e-3)
+
+
+def test_compressor_channels_last_matches_default_layout():
+    """The -m 3 model with use_channels_last(): same loss and gradients as the NCHW run (convolutions pick other cuDNN
+    kernels, so equality is numerical), likelihood shapes unchanged."""
+    torch.manual_seed(44)
+    tasks = ("rgb", "depth_euclidean", "normal")
+    a = mm.build_compressor(3, tasks, 24, 40, lmbda=1e-2).to(DEV).train()
+    b = mm.build_compressor(3, tasks, 24, 40, lmbda=1e-2)
+    b.load_state_dict(a.state_dict())
+    b.to(DEV).train().use_channels_last()
+    batch = mm.synthetic_batch(tasks, 2, size=256, seed=21, device=DEV)
+    nz = torch.rand(2, 120, 1, 1, device=DEV) - 0.5
+    ny = torch.rand(2, 24, 1, 1, device=DEV) - 0.5
+    losses = []
+    for m in (a, b):
+        c = m.model["compressor"]
+        ef, gf = c.entropy_bottleneck.forward, c.gaussian_conditional.forward
+        c.entropy_bottleneck.forward = lambda x, training=None, ef=ef: ef(x, training, noise=nz)
+        c.gaussian_conditional.forward = lambda y, s, means=None, training=None, gf=gf: gf(y, s, means, training, noise=ny)
+        with torch.backends.cudnn.flags(allow_tf32=False):
+            x_hats, lik = m(batch)
+            loss, _ = m.rate_distortion_loss(m._as_model_format(batch), x_hats, lik, "train")
+            loss.backward()
+        losses.append(loss.item())
+        assert lik["y"].shape == (2, 24, 4, 4)
+    assert abs(losses[0] - losses[1]) <= 2e-3 * abs(losses[0])
+    pb = dict(b.named_parameters())
+    worst = 0.0
+    for n, p in a.named_parameters():
+        if p.grad is None or n.endswith("quantiles"):
+            continue
+        d = p.grad.abs().max().item()
+        if d > 1e-12:
+            worst = max(worst, (p.grad - pb[n].grad.reshape(p.grad.shape)).abs().max().item() / d)
+    assert worst < 3e-2, worst
+    assert x_hats["rgb"].is_contiguous(memory_format=torch.channels_last)
