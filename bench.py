@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--serial-heads", action="store_true",
                     help="run the task heads' GDN sites one after the other on one stream (default: one stream per task head)")
     ap.add_argument("--precision", default="auto", help="GDN contraction: auto | fp32 | tf32 | 3xtf32")
+    ap.add_argument("--layout", default="channels_last", choices=["nchw", "channels_last"],
+                    help="memory format of the end-to-end step (the rate-path `value` always runs the NCHW kernels)")
     return ap.parse_args()
 
 
@@ -701,6 +703,7 @@ def measure_config(name, args, env, steps, warmup, headline):
     model.update_bottleneck_values()  # CPU, before .to(device): the reference's order (src/compress.py:101-105)
     model.to(device)
     model.train(train)
+    torch.cuda.reset_peak_memory_stats(device)
     dp = mm.DataParallel(model) if (world > 1 and train) else None
     if train:
         model.configure_optimizers(total_steps=10 * (steps + warmup))
@@ -771,6 +774,8 @@ def measure_config(name, args, env, steps, warmup, headline):
         if harness.bucket is not None:
             del harness.bucket
             harness.bucket = None
+        if args.layout == "channels_last":
+            model.use_channels_last()
         host = mm.synthetic_batch(cfg["tasks"], B, seed=21 + rank, pin_memory=True)
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         if dp is not None:  # re-home the gradients of the whole model into DataParallel's bucket
@@ -809,7 +814,7 @@ def measure_config(name, args, env, steps, warmup, headline):
         t_e2e = max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0)) / n_e2e
         res["e2e"] = {"value": world * B / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                       "ms_per_step": t_e2e * 1e3, "steps": n_e2e, "last_loss": last,
-                      "peak_memory_GB": torch.cuda.max_memory_allocated(device) / 1e9,
+                      "peak_memory_GB": torch.cuda.max_memory_allocated(device) / 1e9, "layout": args.layout,
                       "what": ("compressor.training_step(batch)" if train else "compressor.validation_step(batch)") +
                               ": H2D of one pinned batch per step (copy stream, prefetched one step ahead), cuDNN convs (TF32 "
                               "allowed, torch default) + mmnc kernels" +
