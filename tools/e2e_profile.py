@@ -8,6 +8,7 @@ torch.backends.cudnn.benchmark = True
 torch.manual_seed(21)
 model = mm.build_compressor(3, TASKS, 128, 100, lmbda=1e-2)
 model.update_bottleneck_values(); model.to(dev); model.train()
+if "channels_last" in sys.argv: model.use_channels_last()
 model.configure_optimizers(total_steps=100)
 host = mm.synthetic_batch(TASKS, 64, seed=21, pin_memory=True)
 def step():
