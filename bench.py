@@ -72,7 +72,7 @@ def parse():
     ap.add_argument("--serial-heads", action="store_true",
                     help="run the task heads' GDN sites one after the other on one stream (default: one stream per task head)")
     ap.add_argument("--precision", default="auto", help="GDN contraction: auto | fp32 | tf32 | 3xtf32")
-    ap.add_argument("--layout", default="channels_last", choices=["nchw", "channels_last"],
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "channels_last"],
                     help="memory format of the end-to-end step (the rate-path `value` always runs the NCHW kernels)")
     return ap.parse_args()
 

@@ -218,6 +218,13 @@ int mmnc_argmax_sse(const float *logits, const float *target, int64_t B, int K, 
                     float *sse, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * (f1) bias gradient of the convolutions: out[c] = sum over (b, s) of g[b, c, s] for an NCHW tensor (B, C, S).
+ *   workspace: mmnc_channel_sum_workspace_floats(B, C, S) floats.  Fixed-order two-stage reduction (bit-reproducible).
+ * ------------------------------------------------------------------------------------------------------- */
+int64_t mmnc_channel_sum_workspace_floats(int64_t B, int64_t C, int64_t S);
+int mmnc_channel_sum(const float *g, int64_t B, int64_t C, int64_t S, float *workspace, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * (f4) input pipeline — what `get_transform` does per sample on the host (src/datasets/transforms.py:39-131,
  *   src/datasets/clevr.py:48-83), as three kernels over a whole batch of raw decoded pixels:
  *   u8 HWC (B, HW, src_channels) -> f32 (B, dst_channels, HW), value / divisor (255 for ToTensor);

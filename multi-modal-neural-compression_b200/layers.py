@@ -9,21 +9,44 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 from torch import Tensor
 
 from . import ops
 from .entropy_models import LowerBound
 
 
+class _Conv2d(nn.Conv2d):
+    """nn.Conv2d (same parameters, same state-dict keys, the convolution itself on cuDNN) whose bias gradient is
+    reduced by `mmnc_channel_sum` instead of torch's generic reduction: on CUDA the bias is added by a tiny autograd
+    function after the bias-free convolution - which is what torch does internally after a cuDNN convolution."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        if self.bias is None or not x.is_cuda or x.dtype != torch.float32 or ops._is_channels_last(x):
+            return super().forward(x)
+        return ops.bias_add_(self._conv_forward(x, self.weight, None), self.bias)
+
+
+class _ConvTranspose2d(nn.ConvTranspose2d):
+    def forward(self, x: Tensor, output_size=None) -> Tensor:
+        if self.bias is None or not x.is_cuda or x.dtype != torch.float32 or ops._is_channels_last(x):
+            return super().forward(x, output_size)
+        output_padding = self._output_padding(x, output_size, self.stride, self.padding, self.kernel_size, 2,
+                                              self.dilation)
+        out = F.conv_transpose2d(x, self.weight, None, self.stride, self.padding, output_padding, self.groups,
+                                 self.dilation)
+        return ops.bias_add_(out, self.bias)
+
+
 def conv(in_channels, out_channels, kernel_size=5, stride=2):
     """compressai.models.utils.conv — stays on cuDNN (out of the rate path)."""
-    return nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=kernel_size // 2)
+    return _Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=kernel_size // 2)
 
 
 def deconv(in_channels, out_channels, kernel_size=5, stride=2):
     """compressai.models.utils.deconv — stays on cuDNN."""
-    return nn.ConvTranspose2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
-                              output_padding=stride - 1, padding=kernel_size // 2)
+    return _ConvTranspose2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
+                            output_padding=stride - 1, padding=kernel_size // 2)
 
 
 class NonNegativeParametrizer(nn.Module):

@@ -567,6 +567,38 @@ def gdn(x: Tensor, beta_eff: Tensor, gamma_eff: Tensor, inverse: bool, precision
     return _GDNFn.apply(x, beta_eff, gamma_eff, bool(inverse), GDN_PRECISION[precision])
 
 
+# ------------------------------------------------------------------------------------------------ conv bias (f1)
+def channel_sum(g: Tensor) -> Tensor:
+    """(B, C, ...) NCHW -> (C,) sums over batch and space: the bias gradient of a convolution."""
+    _need_cuda(g)
+    g = _f32c(g)
+    B, C, S = _bcs(g)
+    out = torch.empty(C, dtype=torch.float32, device=g.device)
+    ws = torch.empty(int(_lib.lib().mmnc_channel_sum_workspace_floats(B, C, S)), dtype=torch.float32, device=g.device)
+    _lib.check(_lib.lib().mmnc_channel_sum(_p(g), B, C, S, _p(ws), _p(out), _stream()))
+    return out
+
+
+class _BiasAddFn(torch.autograd.Function):
+    """out + bias[None, :, None, None], in place on the convolution's output.  Forward is the element-wise add torch
+    issues after a cuDNN convolution anyway; the backward replaces torch's generic reduction for the bias gradient
+    with `mmnc_channel_sum` and passes the output gradient through untouched."""
+
+    @staticmethod
+    def forward(ctx, out, bias):
+        ctx.mark_dirty(out)
+        out.add_(bias.view(1, -1, *([1] * (out.dim() - 2))))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, (channel_sum(g) if ctx.needs_input_grad[1] else None)
+
+
+def bias_add_(out: Tensor, bias: Tensor) -> Tensor:
+    return _BiasAddFn.apply(out, bias)
+
+
 # ------------------------------------------------------------------------------------------------ coding (a9-a12)
 def pmf_to_quantized_cdf(pmf: Sequence[float], precision: int = 16) -> List[int]:
     """compressai._CXX.pmf_to_quantized_cdf look-alike (host function of the C ABI)."""

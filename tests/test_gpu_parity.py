@@ -921,4 +921,26 @@ def test_compressor_channels_last_matches_default_layout():
         if d > 1e-12:
             worst = max(worst, (p.grad - pb[n].grad.reshape(p.grad.shape)).abs().max().item() / d)
     assert worst < 3e-2, worst
-    assert x_hats["rgb"].is_contiguous(memory_format=torch.channels_last)
+
+
+def test_conv_bias_gradient_kernel_matches_torch():
+    """(f1) The convolutions' bias gradient through mmnc_channel_sum: same numbers as torch's own reduction, forward
+    output identical to nn.Conv2d / nn.ConvTranspose2d, bit-reproducible run to run."""
+    torch.manual_seed(51)
+    for shape in ((5, 7, 33, 20), (64, 50, 64, 64), (3, 300, 1, 1), (2, 1, 256, 256)):
+        g = torch.randn(*shape, device=DEV)
+        got, want = mm.ops.channel_sum(g), g.sum(dim=(0, 2, 3))
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-3 * g[:, 0].numel() ** 0.5)
+        assert torch.equal(got, mm.ops.channel_sum(g))
+    for ours, ref, x in ((mm.conv(6, 10), torch.nn.Conv2d(6, 10, 5, 2, 2), torch.randn(3, 6, 32, 32)),
+                         (mm.deconv(6, 10), torch.nn.ConvTranspose2d(6, 10, 5, 2, 2, 1), torch.randn(3, 6, 16, 16))):
+        ref.load_state_dict(ours.state_dict())
+        ours.to(DEV), ref.to(DEV)
+        xa, xb = x.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+        with torch.backends.cudnn.flags(allow_tf32=False):
+            ya, yb = ours(xa), ref(xb)
+            w = torch.randn_like(ya)
+            ya.backward(w), yb.backward(w)
+        assert torch.allclose(ya, yb, rtol=1e-5, atol=1e-6) and torch.allclose(xa.grad, xb.grad, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(ours.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-4)
+        assert torch.allclose(ours.weight.grad, ref.weight.grad, rtol=1e-4, atol=1e-4)
