@@ -223,6 +223,8 @@ int mmnc_argmax_sse(const float *logits, const float *target, int64_t B, int K, 
  * ------------------------------------------------------------------------------------------------------- */
 int64_t mmnc_channel_sum_workspace_floats(int64_t B, int64_t C, int64_t S);
 int mmnc_channel_sum(const float *g, int64_t B, int64_t C, int64_t S, float *workspace, float *out, void *stream);
+/* x[b, c, s] += bias[c] in place on an NCHW tensor (the add torch issues after a bias-free cuDNN convolution). */
+int mmnc_bias_add(float *x, const float *bias, int64_t B, int64_t C, int64_t S, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * (f4) input pipeline — what `get_transform` does per sample on the host (src/datasets/transforms.py:39-131,

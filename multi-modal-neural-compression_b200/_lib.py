@@ -65,6 +65,7 @@ SIGNATURES = {
     "mmnc_nonneg_reparam_backward": (I32, [VP, VP, I64, F32, VP, VP]),
     "mmnc_channel_sum_workspace_floats": (I64, [I64, I64, I64]),
     "mmnc_channel_sum": (I32, [VP, I64, I64, I64, VP, VP, VP]),
+    "mmnc_bias_add": (I32, [VP, VP, I64, I64, I64, VP]),
     "mmnc_argmax_sse": (I32, [VP, VP, I64, I32, I64, VP, VP, VP]),
     "mmnc_prep_u8_hwc_to_f32_chw": (I32, [VP, I64, I64, I32, I32, F32, VP, VP]),
     "mmnc_prep_u16_to_f32": (I32, [VP, I64, F32, VP, VP]),

@@ -128,3 +128,42 @@ extern "C" int mmnc_channel_sum(const float *g, int64_t B, int64_t C, int64_t S,
         workspace, C, splits, out);
     return after_launch("channel_sum_finish_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// In-place per-channel bias add on an NCHW tensor: x[b, c, s] += bias[c].  torch adds the bias with a generic
+// broadcasting element-wise kernel after every cuDNN convolution (3.8 ms per training step of config C2, 2.5 TB/s);
+// this one streams float4 along the contiguous planes.
+namespace mmnc {
+
+__global__ void __launch_bounds__(256)
+bias_add_kernel(float *__restrict__ x, const float *__restrict__ bias, int64_t BC, int64_t C, int64_t S) {
+    const bool vec = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (vec) {
+        const int64_t q = S >> 2, n4 = BC * q;
+        float4 *x4 = reinterpret_cast<float4 *>(x);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+            const float b = __ldg(bias + (i / q) % C);
+            float4 v = x4[i];
+            v.x += b; v.y += b; v.z += b; v.w += b;
+            x4[i] = v;
+        }
+    } else {
+        const int64_t n = BC * S;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+            x[i] += __ldg(bias + (i / S) % C);
+    }
+}
+
+}  // namespace mmnc
+
+extern "C" int mmnc_bias_add(float *x, const float *bias, int64_t B, int64_t C, int64_t S, void *stream) {
+    MMNC_REQUIRE(B >= 0 && C >= 0 && S >= 0, "bias_add: negative dimension");
+    if (B * C * S == 0) return MMNC_OK;
+    MMNC_REQUIRE(x && bias, "bias_add: null pointer");
+    const int64_t work = (S % 4 == 0) ? B * C * S / 4 : B * C * S;
+    int64_t blocks = (work + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    bias_add_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, bias, B * C, C, S);
+    return after_launch("bias_add_kernel");
+}

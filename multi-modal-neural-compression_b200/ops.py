@@ -587,7 +587,11 @@ class _BiasAddFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, out, bias):
         ctx.mark_dirty(out)
-        out.add_(bias.view(1, -1, *([1] * (out.dim() - 2))))
+        if out.is_contiguous() and out.dtype == torch.float32 and bias.dtype == torch.float32 and bias.is_contiguous():
+            B, C, S = _bcs(out)
+            _lib.check(_lib.lib().mmnc_bias_add(_p(out), _p(bias), B, C, S, _stream()))
+        else:
+            out.add_(bias.view(1, -1, *([1] * (out.dim() - 2))))
         return out
 
     @staticmethod
