@@ -234,7 +234,7 @@ class RatePathHarness:
         L, prec = mm._lib.lib(), mm.ops.GDN_PRECISION[precision]
         fam_f = {0: "streaming (C<=4)", 1: "fp32 SIMT", 2: "tcgen05", 3: "tcgen05 + TMA in/out"}
         fam_b = {0: "streaming (C<=4)", 1: "fp32 SIMT", 2: "fused tcgen05", 3: "fused tcgen05 + TMA, pipelined",
-                 4: "fused tcgen05 + TMA, streamed gamma"}
+                 4: "fused tcgen05 + TMA, streamed gamma", 5: "fused tcgen05 + TMA, streamed gamma + x prefetch"}
         rows = {}
         for mod, x, g, _, _ in self.sites:
             B, C = x.shape[:2]
@@ -306,7 +306,8 @@ def roofline_of_gdn(torch, mm, harness, peak_gbs, peak_src, precision):
     shape = "GDN(%d) on %dx%d, batch %d" % (C, x0.shape[2], x0.shape[3], B)
     # DRAM bytes of exactly this launch from `ncu --set full` (profiles/r01_ncu_summary.md); other shapes: unknown
     ncu_traffic = {(64, 50, 65536): (2.480e9, 1.632e9)}.get((B, C, HW), (None, None))
-    fam = {4: "TMA-fed, streamed gamma", 3: "TMA-fed pipelined", 2: "first generation"}.get(variant, "variant %d" % variant)
+    fam = {5: "TMA-fed, streamed gamma + x prefetch", 4: "TMA-fed, streamed gamma", 3: "TMA-fed pipelined",
+           2: "first generation"}.get(variant, "variant %d" % variant)
     bwd_roof = {
         "bound": "hbm", "kernel": "gdn backward (fused tcgen05, %s), %s; includes its ~10 us partial-reduce launch" % (fam, shape),
         "achieved": 12.0 * n / t_b / 1e9, "peak": peak_gbs, "unit": "GB/s", "frac": 12.0 * n / t_b / 1e9 / peak_gbs,

@@ -173,7 +173,8 @@ int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int6
 /* Which kernel family mmnc_gdn_backward would launch for these arguments (diagnostics / tests):
  * 0 = streaming (C <= 4), 1 = fp32 SIMT, 2 = fused tcgen05, 3 = fused tcgen05 fed by TMA and software-pipelined
  * (needs HW % 128 == 0 and 16-byte aligned x / g), 4 = the same kernel with the gamma operand streamed through one
- * shared-memory buffer (112 <= C <= 128). */
+ * shared-memory buffer (112 <= C <= 128), 5 = streamed gamma + a second x buffer so that the next tile's x lands while
+ * the current one computes (80 <= C <= 111, at least three tiles per CTA). */
 int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, int precision);
 /* Same for mmnc_gdn_forward: 0 = streaming, 1 = fp32 SIMT, 2 = tcgen05 (per-thread global loads), 3 = tcgen05 with
  * TMA in / TMA out. */

@@ -54,6 +54,7 @@ bool gdn_tc_forward2_supported(const float *x, const float *y, int64_t B, int64_
 // gdn_tc_bwd2.cu
 bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64_t C, int64_t HW);
 bool gdn_tc_backward2_streams(int64_t C);
+bool gdn_tc_backward2_prefetches(int64_t B, int64_t C, int64_t HW);
 int gdn_tc_backward2(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
                      float *, void *, size_t, cudaStream_t);
 // gdn_tc_bwd.cu
@@ -145,7 +146,8 @@ extern "C" int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t
                                          int precision) {
     if (gdn_small_supported(C)) return 0;
     if (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) {
-        if (gdn_tc_backward2_supported(x, g, B, C, HW)) return gdn_tc_backward2_streams(C) ? 4 : 3;
+        if (gdn_tc_backward2_supported(x, g, B, C, HW))
+            return gdn_tc_backward2_streams(C) ? 4 : (gdn_tc_backward2_prefetches(B, C, HW) ? 5 : 3);
         if (gdn_tc_backward_supported(B, C, HW)) return 2;
     }
     return 1;

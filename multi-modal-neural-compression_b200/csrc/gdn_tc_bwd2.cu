@@ -25,6 +25,10 @@
 //     back) by cp.async.bulk copies of a pre-packed image of both tiles (a small pack kernel writes them, already in
 //     the core-matrix layout, into the workspace: 2 x 81 KB that stay in L2).  The refill is issued by the leader the
 //     moment the MMA that read the buffer has retired and lands behind the epilogue that follows.
+//   * layers with 80 <= C <= 111 used to run with a single landing stage (two do not fit next to gamma and gamma^T), so
+//     every tile waited for its own x to arrive.  Streaming the gamma operand frees enough shared memory for a SECOND
+//     x buffer: x of tile k + 1 lands while tile k computes (its A fill and MMA1 need nothing else), g follows as soon
+//     as MMA3 of tile k has released the single u buffer (kXPF).  Used when a CTA has at least three tiles.
 // Requires HW % 128 == 0 (a 128-pixel tile never straddles two images) and 16-byte aligned tensors; everything else
 // stays on gdn_tc_bwd.cu.
 #include <cuda.h>  // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
@@ -130,6 +134,48 @@ __device__ __forceinline__ void bwd2_issue_tile(const volatile Bwd2Ctx &t, int k
             : "memory");
 }
 
+// x-prefetch mode (kXPF): shared memory is [u | x2 (even tiles) | x2 (odd tiles)]; x of tile k lands in buffer k & 1 on
+// its own barrier (full_bar[0] / full_bar[2]), g of every tile in the single u buffer on full_bar[1].
+__device__ __forceinline__ void bwd2_tile_coords(const volatile Bwd2Ctx &t, int k, int *b, int *hw0) {
+    const uint32_t tile = blockIdx.x + (uint32_t)k * gridDim.x;
+    const uint32_t bb = tile / (uint32_t)t.tiles_per_img;
+    *b = (int)bb;
+    *hw0 = (int)(tile - bb * (uint32_t)t.tiles_per_img) * tcb2::TILE;
+}
+__device__ __forceinline__ void bwd2_issue_x(const volatile Bwd2Ctx &t, int k) {
+    int b, hw0;
+    bwd2_tile_coords(t, k, &b, &hw0);
+    const uint32_t R8 = (uint32_t)t.R8, buf_bytes = R8 * 4096u;
+    const uint32_t bar = t.full_bar0 + 16u * (uint32_t)(k & 1), dst = t.stage0 + buf_bytes * (1u + (uint32_t)(k & 1));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)t.C * 512u) : "memory");
+    const uint64_t tm = reinterpret_cast<uint64_t>(t.tm_x);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(dst + (uint32_t)a * R8 * 1024u), "l"(tm), "r"(hw0 + 32 * a), "r"(0), "r"(b), "r"(bar)
+            : "memory");
+}
+__device__ __forceinline__ void bwd2_issue_g(const volatile Bwd2Ctx &t, int k) {
+    int b, hw0;
+    bwd2_tile_coords(t, k, &b, &hw0);
+    const uint32_t R8 = (uint32_t)t.R8;
+    const uint32_t bar = t.full_bar0 + 8u, dst = t.stage0;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)t.C * 512u) : "memory");
+    const uint64_t tm = reinterpret_cast<uint64_t>(t.tm_g);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(dst + (uint32_t)a * R8 * 1024u), "l"(tm), "r"(hw0 + 32 * a), "r"(0), "r"(b), "r"(bar)
+            : "memory");
+}
+// the single u buffer and the x buffer of tile k are free (MMA3 of tile k has retired): g of the next tile, x of the one after
+__device__ __forceinline__ void bwd2_refill_xpf(const volatile Bwd2Ctx &t, int k) {
+    if (k + 1 < t.n_k) bwd2_issue_g(t, k + 1);
+    if (k + 2 < t.n_k) bwd2_issue_x(t, k + 2);
+}
+
 // compile-time unrolled MMA chains (every per-step offset is an immediate inside the asm block, see tc_ptx.cuh)
 template <int KS, int NK>
 __device__ __forceinline__ void mma_ts_chain(uint32_t d, uint32_t a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
@@ -163,8 +209,9 @@ __device__ __forceinline__ void tmem_stw(uint32_t taddr, const uint32_t (&r)[W])
 // the instruction footprint inside the instruction cache (ncu: 21 % of the stalls were instruction fetches with two
 // copies).  Channel offsets are folded into the per-thread TMEM / shared / global bases; only the last 16 channels of
 // a thread can be padding, and a 16-bit mask says which.
-template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse, bool kStream>
+template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse, bool kStream, bool kXPF>
 __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int group, int tg, uint32_t tmem_base_in) {
+    static_assert(!kXPF || (kStream && NGROUPS == 1 && NSTAGES == 1), "x prefetch: one group, one u buffer, streamed gamma");
     using namespace tc;
     using namespace tcb2;
     constexpr int P = KH8 * 16;   // padded channel count
@@ -230,9 +277,12 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     for (int k = group; k < t.n_k; k += NGROUPS) {
         const int s = k % NSTAGES;
         const uint32_t buf_bytes = (uint32_t)t.R8 * 4096u;
-        const uint32_t us = t.stage0 + (uint32_t)s * 2u * buf_bytes, xs = us + buf_bytes;
+        const uint32_t us = t.stage0 + (kXPF ? 0u : (uint32_t)s * 2u * buf_bytes);
+        const uint32_t xs = kXPF ? t.stage0 + buf_bytes * (1u + (uint32_t)(k & 1)) : us + buf_bytes;
         const uint32_t uq = us + bq, xq = xs + bq;
-        const uint32_t bar_x = t.full_bar0 + 16u * (uint32_t)s, fpar = (uint32_t)((k / NSTAGES) & 1);
+        const uint32_t bar_x = t.full_bar0 + 16u * (uint32_t)(kXPF ? (k & 1) : s);
+        const uint32_t bar_g = kXPF ? t.full_bar0 + 8u : bar_x + 8u;
+        const uint32_t fpar = (uint32_t)(((kXPF ? (k >> 1) : (k / NSTAGES))) & 1), gpar = kXPF ? (uint32_t)(k & 1) : fpar;
         mbar_wait_addr(bar_x, fpar);
         // ---- this thread's channels of x out of the landing buffer (conflict-free: a warp reads one 128 B row)
         float xv[KH], gv[KG];
@@ -272,7 +322,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
             }
         }
         // g has had the A fill and the MMA1 issue to land behind x
-        mbar_wait_addr(bar_x + 8u, fpar);
+        mbar_wait_addr(bar_g, gpar);
         if constexpr (!PARK) {
             MMNC_FRESH_OI();
 #pragma unroll
@@ -360,7 +410,8 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                 // single stage: the next tile's load can only start when MMA3 has retired, and every cycle until then
                 // is exposed - poll between the blocks of this epilogue instead of finishing it first
                 if (NSTAGES == 1 && leader && !refilled && mbar_test_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1))) {
-                    if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
+                    if constexpr (kXPF) bwd2_refill_xpf(t, k);
+                    else if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
                     refilled = true;
                 }
             }
@@ -374,7 +425,8 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                 pending = k;
             } else if (!refilled) {
                 mbar_wait_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1));
-                if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
+                if constexpr (kXPF) bwd2_refill_xpf(t, k);
+                else if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
             }
         }
         first = false;
@@ -395,7 +447,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     return first;
 }
 
-template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse, bool kStream>
+template <int KH8, int NGROUPS, int NSTAGES, int TPP, bool kInverse, bool kStream, bool kXPF = false>
 __global__ void __launch_bounds__(NGROUPS * TPP * 128, 1)
 gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_g,
                         int ntiles, int tiles_per_img, int HW, const GdnParams prm, float *__restrict__ dx,
@@ -406,7 +458,8 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     constexpr int TPG = 128 * TPP;
     constexpr int THREADS = NGROUPS * TPG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[2 * NSTAGES];  // [stage][x, g]
+    constexpr int NBUFS = kXPF ? 3 : 2 * NSTAGES;  // landing buffers: [u | x2] per stage, or [u | x2 | x2] with x prefetch
+    __shared__ uint64_t full_bar[kXPF ? 4 : 2 * NSTAGES];  // [stage][x, g]; x prefetch: x even, g, x odd, unused
     __shared__ uint64_t mma_bar[NGROUPS];
     __shared__ uint64_t free_bar[NGROUPS];
     __shared__ uint64_t bfull_bar;
@@ -415,7 +468,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     const int R8 = (C + 1 + 7) >> 3;
     const uint32_t buf_bytes = (uint32_t)R8 * 4096u;  // 4 K atoms of 32 pixels, R8 swizzle atoms of 8 rows each
     const uint32_t stage_bytes = 2u * buf_bytes;      // [u | x2]
-    float *Bs = reinterpret_cast<float *>(smem + (size_t)NSTAGES * stage_bytes);  // gamma   (N = i, K = j)
+    float *Bs = reinterpret_cast<float *>(smem + (size_t)NBUFS * buf_bytes);  // gamma   (N = i, K = j)
     float *Bs2 = Bs + P * P;                                                        // gamma^T (N = k, K = i)
     const int warp = threadIdx.x >> 5;
     const int group = threadIdx.x / TPG, tg = threadIdx.x % TPG;
@@ -423,7 +476,7 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     __shared__ Bwd2Ctx ctx_s;
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2 * NSTAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < (kXPF ? 4 : 2 * NSTAGES); ++s) mbar_init(&full_bar[s], 1);
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&mma_bar[q], 1);
         for (int q = 0; q < NGROUPS; ++q) mbar_init(&free_bar[q], 1);
         mbar_init(&bfull_bar, 1);
@@ -452,8 +505,13 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     // box writes rows < C only, the loop below initialises rows >= C only
     if (threadIdx.x == 0) {
         const int n_k = ctx.n_k;
-        const int pre = n_k < NSTAGES ? n_k : NSTAGES;
-        for (int k = 0; k < pre; ++k) bwd2_issue_tile<NSTAGES>(ctx, k);
+        if constexpr (kXPF) {
+            if (n_k > 0) { bwd2_issue_x(ctx, 0); bwd2_issue_g(ctx, 0); }
+            if (n_k > 1) bwd2_issue_x(ctx, 1);
+        } else {
+            const int pre = n_k < NSTAGES ? n_k : NSTAGES;
+            for (int k = 0; k < pre; ++k) bwd2_issue_tile<NSTAGES>(ctx, k);
+        }
         if (kStream && n_k > 0) bwd2_load_b<P>(ctx, 0);  // gamma for the first MMA1
     }
     // gamma tiles, as in gdn_tc_bwd.cu: Bs[n/8][k/4][n%8][k%4] = tf32(gamma[n][k]); column k = C holds beta
@@ -495,21 +553,22 @@ gdn_tc_backward2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     {
         const int pad_rows = 8 * R8 - C;                                   // 1 .. 8
         const uint32_t per_buf = 4u * (uint32_t)pad_rows * 32u;            // 4 K atoms x pad rows x 32 words
-        const uint32_t words = (uint32_t)NSTAGES * 2u * per_buf;
+        const uint32_t words = (uint32_t)NBUFS * per_buf;
         for (uint32_t i = threadIdx.x; i < words; i += THREADS) {
             const uint32_t buf = i / per_buf, o = i - buf * per_buf;
             const uint32_t atom = o / ((uint32_t)pad_rows * 32u), o2 = o - atom * (uint32_t)pad_rows * 32u;
             const int r = C + (int)(o2 >> 5);
             const uint32_t w = o2 & 31u;
             const uint32_t byte = buf * buf_bytes + ((atom * (uint32_t)R8 + (uint32_t)(r >> 3)) << 10) + ((uint32_t)(r & 7) << 7) + (w << 2);
-            *reinterpret_cast<uint32_t *>(smem + byte) = ((buf & 1u) && r == C) ? 0x3f800000u : 0u;
+            const bool is_x2 = kXPF ? (buf >= 1u) : ((buf & 1u) != 0u);
+            *reinterpret_cast<uint32_t *>(smem + byte) = (is_x2 && r == C) ? 0x3f800000u : 0u;
         }
     }
     fence_async_smem();
     fence_before();
     __syncthreads();
     fence_after();
-    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, TPP, kInverse, kStream>(ctx, group, tg, tmem_base_s);
+    const bool first = bwd2_group_loop<KH8, NGROUPS, NSTAGES, TPP, kInverse, kStream, kXPF>(ctx, group, tg, tmem_base_s);
     // ---- this group's partial d gamma / d beta: D3 lane i = out channel, column j = in channel (j = C: d beta)
     float *dst = part + ((int64_t)blockIdx.x * NGROUPS + group) * C * (C + 1);
     const int pix = tg & 127;
@@ -627,6 +686,27 @@ bool gdn_tc_backward2_supported(const float *x, const float *g, int64_t B, int64
     return tmah::encode_tiled() != nullptr;
 }
 
+// x-prefetch variant of the single-stage layers (80 <= C <= 111): [u | x2 | x2] + ONE streamed gamma buffer.  Worth it
+// only when a CTA walks through several tiles (the pack kernel and the per-tile refills of gamma cost a little).
+static bool bwd2_xpf_geometry(int64_t C, int64_t ntiles, const Bwd2Geometry &geo, size_t *smem) {
+    static const bool enabled = []() { const char *e = getenv("MMNC_GDN_XPF"); return !(e && !strcmp(e, "0")); }();
+    if (!enabled || geo.stream || geo.groups != 1 || geo.stages != 1) return false;
+    if (ntiles < 3 * (int64_t)sm_count()) return false;
+    const size_t R8 = (size_t)(C + 1 + 7) / 8, buf = R8 * 4096, gam = (size_t)geo.P * geo.P * 4;
+    size_t bytes = 3 * buf + gam;
+    const size_t over_b = 2 * buf + (3 * R8 + (size_t)geo.P / 8) * 1024, over_a = (3 * R8 + 16) * 1024;
+    if (bytes < over_b) bytes = over_b;
+    if (bytes < over_a) bytes = over_a;
+    *smem = bytes + 1024;
+    return *smem + 256 <= 227 * 1024;
+}
+
+bool gdn_tc_backward2_prefetches(int64_t B, int64_t C, int64_t HW) {
+    Bwd2Geometry geo;
+    size_t smem;
+    return bwd2_geometry(C, &geo) && bwd2_xpf_geometry(C, B * HW / tcb2::TILE, geo, &smem);
+}
+
 bool gdn_tc_backward2_streams(int64_t C) {
     Bwd2Geometry geo;
     return bwd2_geometry(C, &geo) && geo.stream;
@@ -636,7 +716,8 @@ size_t gdn_tc_backward2_workspace(int64_t B, int64_t C, int64_t HW) {
     Bwd2Geometry geo;
     if (!bwd2_geometry(C, &geo)) return 0;
     (void)B; (void)HW;
-    const size_t packed = geo.stream ? 2 * sizeof(float) * (size_t)geo.P * geo.P + 256 : 0;
+    const bool may_stream = geo.stream || (geo.groups == 1 && geo.stages == 1);  // streamed gamma or the x-prefetch variant
+    const size_t packed = may_stream ? 2 * sizeof(float) * (size_t)geo.P * geo.P + 256 : 0;
     return sizeof(float) * (size_t)sm_count() * geo.groups * C * (C + 1) + 256 + packed;
 }
 
@@ -669,7 +750,11 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
     const int tpp = 2;
 #define MMNC_PICK(N, G, S) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, true, false> : (Kernel)gdn_tc_backward2_kernel<N, G, S, 2, false, false>)
 #define MMNC_PICK_STREAM(N) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, 1, 1, 2, true, true> : (Kernel)gdn_tc_backward2_kernel<N, 1, 1, 2, false, true>)
-    const int key = (geo.stream ? 1000 : 0) + (geo.P / 16) * 100 + geo.groups * 10 + geo.stages;
+#define MMNC_PICK_XPF(N) (inverse ? (Kernel)gdn_tc_backward2_kernel<N, 1, 1, 2, true, true, true> : (Kernel)gdn_tc_backward2_kernel<N, 1, 1, 2, false, true, true>)
+    size_t xpf_smem = 0;
+    const bool xpf = bwd2_xpf_geometry(C, ntiles, geo, &xpf_smem);
+    if (xpf) { geo.smem = xpf_smem; geo.stream = true; }
+    const int key = (xpf ? 2000 : (geo.stream ? 1000 : 0)) + (geo.P / 16) * 100 + geo.groups * 10 + geo.stages;
     switch (key) {
         case 223: kernel = MMNC_PICK(2, 2, 3); break;
         case 323: kernel = MMNC_PICK(3, 2, 3); break;
@@ -679,10 +764,13 @@ int gdn_tc_backward2(const float *x, const float *g, int64_t B, int64_t C, int64
         case 711: kernel = MMNC_PICK(7, 1, 1); break;
         case 1811: kernel = MMNC_PICK_STREAM(8); break;   // C = 112 .. 127
         case 1911: kernel = MMNC_PICK_STREAM(9); break;   // C = 128
+        case 2611: kernel = MMNC_PICK_XPF(6); break;      // C = 80 .. 95, long tile sequences
+        case 2711: kernel = MMNC_PICK_XPF(7); break;      // C = 96 .. 111, long tile sequences
         default: break;
     }
 #undef MMNC_PICK
 #undef MMNC_PICK_STREAM
+#undef MMNC_PICK_XPF
     if (kernel == nullptr) {
         set_error("gdn_tc_backward2: no kernel instance for C = %lld (P %d, groups %d, stages %d)", (long long)C, geo.P,
                   geo.groups, geo.stages);

@@ -29,7 +29,7 @@ REAL_CONFIGS = {
 
 
 # fused backward variant the GDN(c) @ 128 x 128 layer of each configuration must take (3 = TMA-fed tcgen05 kernel)
-WIDE_VARIANT = {100: 3, 128: 4}
+WIDE_VARIANT = {100: 3, 128: 4}  # batch 2 here: too few tiles per CTA for the x-prefetch variant (5)
 
 
 def _pair(name, seed):

@@ -466,7 +466,8 @@ def test_gdn_backward_pipelined_long_sequences(shape):
     ours, _ = _pair_gdn(C, False, precision="tf32")
     x = torch.randn(*shape, device=DEV)
     g = torch.randn(*shape, device=DEV)
-    assert _gdn_bwd_variant(x, g) == 3
+    # C = 100 with >= 3 tiles per CTA takes the x-prefetch variant (5): second x buffer + streamed gamma
+    assert _gdn_bwd_variant(x, g) == (5 if C == 100 else 3)
     beta, gamma = ours.beta_reparam(ours.beta).detach(), ours.gamma_reparam(ours.gamma).detach()
     outs = []
     for prec in ("tf32", "tf32", "fp32"):
@@ -517,7 +518,7 @@ def test_gdn_tensor_core_full_size_properties(shape):
     beta, gamma = ours.beta_reparam(ours.beta).detach(), ours.gamma_reparam(ours.gamma).detach()
     x = torch.randn(*shape, device=DEV)
     g = torch.randn(*shape, device=DEV)
-    assert _gdn_bwd_variant(x, g) == 3
+    assert _gdn_bwd_variant(x, g) == (5 if C == 100 else 3)
 
     def run(xi, gi):
         xr, br, gr = xi.clone().requires_grad_(True), beta.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
