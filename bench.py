@@ -816,7 +816,8 @@ def measure_config(name, args, env, steps, warmup, headline):
         res["e2e"] = {"value": world * B / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                       "ms_per_step": t_e2e * 1e3, "steps": n_e2e, "last_loss": last,
                       "peak_memory_GB": torch.cuda.max_memory_allocated(device) / 1e9, "layout": args.layout,
-                      "what": ("compressor.training_step(batch)" if train else "compressor.validation_step(batch)") +
+                      "what": ("compressor.training_step(batch)" if train else
+                               "compressor.validation_step(batch) incl. PSNR + MS-SSIM of every task (the reference's validation step)") +
                               ": H2D of one pinned batch per step (copy stream, prefetched one step ahead), cuDNN convs (TF32 "
                               "allowed, torch default) + mmnc kernels" +
                               (", backward, gradient all-reduce (N>1), both Adam steps" if train else "") + ", loss.item()"}
