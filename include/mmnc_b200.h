@@ -174,11 +174,24 @@ int mmnc_gdn_backward(const float *x, const float *g, int64_t B, int64_t C, int6
  * 0 = streaming (C <= 4), 1 = fp32 SIMT, 2 = fused tcgen05, 3 = fused tcgen05 fed by TMA and software-pipelined
  * (needs HW % 128 == 0 and 16-byte aligned x / g), 4 = the same kernel with the gamma operand streamed through one
  * shared-memory buffer (112 <= C <= 128), 5 = streamed gamma + a second x buffer so that the next tile's x lands while
- * the current one computes (80 <= C <= 111, at least three tiles per CTA). */
+ * the current one computes (80 <= C <= 111, at least three tiles per CTA), 6 = the wide-layer pair (129 <= C <= 256,
+ * HW % 32 == 0): a dx kernel with BOTH gamma operands streamed in K chunks through a shared-memory ring, u written to
+ * the workspace, and a split-K tcgen05 GEMM over pixels for d gamma / d beta. */
 int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t B, int64_t C, int64_t HW, int precision);
 /* Same for mmnc_gdn_forward: 0 = streaming, 1 = fp32 SIMT, 2 = tcgen05 (per-thread global loads), 3 = tcgen05 with
- * TMA in / TMA out. */
+ * TMA in / TMA out, 6 = the wide-layer kernel (129 <= C <= 256, gamma streamed in K chunks; needs the workspace of the
+ * _ws entry points below). */
 int mmnc_gdn_forward_variant(const float *x, const float *y, int64_t B, int64_t C, int64_t HW, int precision);
+/* Forward with a scratch buffer.  Layers of 129 .. 256 channels (IGDN(256) of config C3) run on the tensor cores only
+ * through these: gamma no longer fits shared memory, so it is packed once per call into `workspace`
+ * (mmnc_gdn_forward_workspace_bytes, 0 when the shape needs none) and streamed from there.  With workspace = NULL they
+ * behave exactly like the calls without the suffix (fp32 SIMT kernel for such layers). */
+size_t mmnc_gdn_forward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int precision);
+int mmnc_gdn_forward_ws(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta, const float *gamma,
+                        int inverse, int precision, float *y, void *workspace, size_t workspace_bytes, void *stream);
+int mmnc_gdn_forward_raw_ws(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
+                            const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal, int inverse,
+                            int precision, float *y, void *workspace, size_t workspace_bytes, void *stream);
 /* Same two calls taking the RAW parameters of compressai.layers.GDN (`beta`, `gamma` as stored in the state dict):
  * the NonNegativeParametrizer re-parametrisation (effective = max(p, bound)^2 - pedestal) is applied while the
  * kernels stage the parameters, and the gradients come back w.r.t. the raw parameters with LowerBound's custom

@@ -57,6 +57,14 @@ bool gdn_tc_backward2_streams(int64_t C);
 bool gdn_tc_backward2_prefetches(int64_t B, int64_t C, int64_t HW);
 int gdn_tc_backward2(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
                      float *, void *, size_t, cudaStream_t);
+// gdn_tc_wide.cu
+size_t gdn_tc_wide_forward_workspace(int64_t B, int64_t C, int64_t HW);
+bool gdn_tc_wide_forward_supported(int64_t B, int64_t C, int64_t HW, const void *workspace, size_t workspace_bytes);
+int gdn_tc_wide_forward(const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, void *, size_t, cudaStream_t);
+bool gdn_tc_wide_backward_supported(const float *x, const float *g, int64_t B, int64_t C, int64_t HW);
+size_t gdn_tc_wide_backward_workspace(int64_t B, int64_t C, int64_t HW);
+int gdn_tc_wide_backward(const float *, const float *, int64_t, int64_t, int64_t, const GdnParams &, int, float *, float *,
+                         float *, void *, size_t, cudaStream_t);
 // gdn_tc_bwd.cu
 bool gdn_tc_backward_supported(int64_t B, int64_t C, int64_t HW);
 size_t gdn_tc_backward_workspace(int64_t B, int64_t C, int64_t HW);
@@ -86,7 +94,8 @@ extern "C" int mmnc_gdn_nhwc_supported(int64_t B, int64_t C, int64_t HW, int pre
 }
 
 static int gdn_forward_impl(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse,
-                            int precision, float *y, void *stream, int nhwc = 0) {
+                            int precision, float *y, void *stream, int nhwc = 0, void *workspace = nullptr,
+                            size_t workspace_bytes = 0) {
     MMNC_REQUIRE(B >= 0 && C >= 0 && HW >= 0, "gdn_forward: negative dimension");
     MMNC_REQUIRE(precision >= 0 && precision <= 3, "gdn_forward: bad precision %d", precision);
     if (B * C * HW == 0) return MMNC_OK;
@@ -104,6 +113,8 @@ static int gdn_forward_impl(const float *x, int64_t B, int64_t C, int64_t HW, co
     const int want = (precision == MMNC_GDN_AUTO) ? MMNC_GDN_TF32 : precision;
     if (want != MMNC_GDN_FP32 && gdn_tc_supported(B, C, HW, want))
         return gdn_tc_forward(x, B, C, HW, prm, inverse, want, y, as_stream(stream));
+    if (want == MMNC_GDN_TF32 && gdn_tc_wide_forward_supported(B, C, HW, workspace, workspace_bytes))  // 129 <= C <= 256
+        return gdn_tc_wide_forward(x, B, C, HW, prm, inverse, y, workspace, workspace_bytes, as_stream(stream));
     return gdn_simt_forward(x, B, C, HW, prm, inverse, y, as_stream(stream));
 }
 
@@ -125,6 +136,27 @@ extern "C" int mmnc_gdn_forward_raw(const float *x, int64_t B, int64_t C, int64_
                             precision, y, stream);
 }
 
+extern "C" size_t mmnc_gdn_forward_workspace_bytes(int64_t B, int64_t C, int64_t HW, int precision) {
+    if (B <= 0 || C <= 0 || HW <= 0) return 0;
+    if (!(precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32)) return 0;
+    return gdn_tc_wide_forward_workspace(B, C, HW);
+}
+
+extern "C" int mmnc_gdn_forward_ws(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta,
+                                   const float *gamma, int inverse, int precision, float *y, void *workspace,
+                                   size_t workspace_bytes, void *stream) {
+    return gdn_forward_impl(x, B, C, HW, gdn_effective(beta, gamma), inverse, precision, y, stream, 0, workspace,
+                            workspace_bytes);
+}
+
+extern "C" int mmnc_gdn_forward_raw_ws(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
+                                       const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal,
+                                       int inverse, int precision, float *y, void *workspace, size_t workspace_bytes,
+                                       void *stream) {
+    return gdn_forward_impl(x, B, C, HW, gdn_raw(beta_raw, gamma_raw, beta_bound, gamma_bound, pedestal), inverse,
+                            precision, y, stream, 0, workspace, workspace_bytes);
+}
+
 extern "C" int mmnc_gdn_forward_raw_nhwc(const float *x, int64_t B, int64_t C, int64_t HW, const float *beta_raw,
                                          const float *gamma_raw, float beta_bound, float gamma_bound, float pedestal,
                                          int inverse, int precision, float *y, void *stream) {
@@ -138,8 +170,11 @@ extern "C" size_t mmnc_gdn_backward_workspace_bytes(int64_t B, int64_t C, int64_
     if (gdn_small_supported(C)) return gdn_small_backward_workspace(B, C, HW);
     // the caller may not know yet whether its tensors will be aligned for the TMA-fed kernel: cover every candidate
     const size_t a = gdn_simt_backward_workspace(B, C, HW), b = gdn_tc_backward_workspace(B, C, HW);
-    const bool tc = (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32) && gdn_tc_backward_supported(B, C, HW);
-    return tc ? b : (a > b ? a : b);
+    const bool tf32 = (precision == MMNC_GDN_AUTO || precision == MMNC_GDN_TF32);
+    const bool tc = tf32 && gdn_tc_backward_supported(B, C, HW);
+    const size_t w = tf32 ? gdn_tc_wide_backward_workspace(B, C, HW) : 0;  // 0 unless 129 <= C <= 256
+    const size_t m = tc ? b : (a > b ? a : b);
+    return m > w ? m : w;
 }
 
 extern "C" int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t B, int64_t C, int64_t HW,
@@ -149,6 +184,7 @@ extern "C" int mmnc_gdn_backward_variant(const float *x, const float *g, int64_t
         if (gdn_tc_backward2_supported(x, g, B, C, HW))
             return gdn_tc_backward2_streams(C) ? 4 : (gdn_tc_backward2_prefetches(B, C, HW) ? 5 : 3);
         if (gdn_tc_backward_supported(B, C, HW)) return 2;
+        if (gdn_tc_wide_backward_supported(x, g, B, C, HW)) return 6;
     }
     return 1;
 }
@@ -157,6 +193,7 @@ extern "C" int mmnc_gdn_forward_variant(const float *x, const float *y, int64_t 
                                         int precision) {
     if (gdn_small_supported(C)) return 0;
     const int want = (precision == MMNC_GDN_AUTO) ? MMNC_GDN_TF32 : precision;
+    if (want == MMNC_GDN_TF32 && !gdn_tc_supported(B, C, HW, want) && gdn_tc_wide_forward_workspace(B, C, HW) > 0) return 6;
     if (want == MMNC_GDN_FP32 || !gdn_tc_supported(B, C, HW, want)) return 1;
     return (want == MMNC_GDN_TF32 && gdn_tc_forward2_supported(x, y, B, C, HW)) ? 3 : 2;
 }
@@ -197,6 +234,9 @@ static int gdn_backward_impl(const float *x, const float *g, int64_t B, int64_t 
         if (gdn_tc_backward_supported(B, C, HW))
             return gdn_tc_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
                                    as_stream(stream));
+        if (gdn_tc_wide_backward_supported(x, g, B, C, HW) && workspace_bytes >= gdn_tc_wide_backward_workspace(B, C, HW))
+            return gdn_tc_wide_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
+                                        as_stream(stream));
     }
     return gdn_simt_backward(x, g, B, C, HW, prm, inverse, dx, dbeta, dgamma, workspace, workspace_bytes,
                              as_stream(stream));

@@ -473,8 +473,9 @@ class _GDNFn(torch.autograd.Function):
         if beta.numel() != C or gamma.shape != (C, C):
             raise ValueError(f"GDN parameters do not match {C} channels")
         y = torch.empty_like(x)
-        _lib.check(_lib.lib().mmnc_gdn_forward(_p(x), B, C, HW, _p(beta), _p(gamma), int(inverse), precision, _p(y),
-                                               _stream()))
+        ws, nbytes = _gdn_forward_workspace(x, B, C, HW, precision)
+        _lib.check(_lib.lib().mmnc_gdn_forward_ws(_p(x), B, C, HW, _p(beta), _p(gamma), int(inverse), precision, _p(y),
+                                                  _p(ws) if ws is not None else None, nbytes, _stream()))
         ctx.save_for_backward(x, beta, gamma)
         ctx.cfg = (B, C, HW, int(inverse), precision)
         return y
@@ -491,6 +492,14 @@ class _GDNFn(torch.autograd.Function):
         _lib.check(_lib.lib().mmnc_gdn_backward(_p(x), _p(g), B, C, HW, _p(beta), _p(gamma), inverse, precision, _p(dx),
                                                 _p(dbeta), _p(dgamma), _p(ws), nbytes, _stream()))
         return dx, dbeta, dgamma, None, None
+
+
+def _gdn_forward_workspace(x: Tensor, B: int, C: int, HW: int, precision: int):
+    """Scratch of the wide-layer forward (129 .. 256 channels: gamma is packed there and streamed); None when not needed."""
+    nbytes = int(_lib.lib().mmnc_gdn_forward_workspace_bytes(B, C, HW, precision))
+    if nbytes == 0:
+        return None, 0
+    return torch.empty(nbytes, dtype=torch.uint8, device=x.device), nbytes
 
 
 def _is_channels_last(x: Tensor) -> bool:
@@ -525,8 +534,10 @@ class _GDNRawFn(torch.autograd.Function):
         else:
             x = x.contiguous()
             y = torch.empty_like(x)
-            _lib.check(L.mmnc_gdn_forward_raw(_p(x), B, C, HW, _p(beta), _p(gamma), beta_bound, gamma_bound, pedestal,
-                                              int(inverse), precision, _p(y), _stream()))
+            ws, nbytes = _gdn_forward_workspace(x, B, C, HW, precision)
+            _lib.check(L.mmnc_gdn_forward_raw_ws(_p(x), B, C, HW, _p(beta), _p(gamma), beta_bound, gamma_bound, pedestal,
+                                                 int(inverse), precision, _p(y), _p(ws) if ws is not None else None,
+                                                 nbytes, _stream()))
             if cl:
                 y = y.contiguous(memory_format=torch.channels_last)
         ctx.save_for_backward(x, beta, gamma)

@@ -289,7 +289,8 @@ def test_gdn_forward_tensor_core(shape, inverse, precision, rtol):
     before = mm.launch_count()
     y = ours(x.to(DEV))
     torch.cuda.synchronize()
-    assert mm.launch_count() == before + 1, "re-parametrisation is fused: one launch per GDN forward"
+    wide = precision == "tf32" and shape[1] > 128  # 129 .. 256 channels: pack gamma + the streamed-operand kernel
+    assert mm.launch_count() == before + (2 if wide else 1), "re-parametrisation is fused: one launch per GDN forward"
     if precision == "3xtf32" and shape[1] > 160:
         rtol = 2e-5  # too many TMEM columns for the split: dispatches to the fp32 SIMT kernel, same tolerance
     want = ref(x)
