@@ -232,9 +232,11 @@ class RatePathHarness:
         """Unique GDN layer shapes of the step with the kernel family each one takes (diagnostic entry points)."""
         mm = self.mm
         L, prec = mm._lib.lib(), mm.ops.GDN_PRECISION[precision]
-        fam_f = {0: "streaming (C<=4)", 1: "fp32 SIMT", 2: "tcgen05", 3: "tcgen05 + TMA in/out"}
+        fam_f = {0: "streaming (C<=4)", 1: "fp32 SIMT", 2: "tcgen05", 3: "tcgen05 + TMA in/out",
+                 6: "tcgen05, gamma streamed in K chunks (129-256 ch)"}
         fam_b = {0: "streaming (C<=4)", 1: "fp32 SIMT", 2: "fused tcgen05", 3: "fused tcgen05 + TMA, pipelined",
-                 4: "fused tcgen05 + TMA, streamed gamma", 5: "fused tcgen05 + TMA, streamed gamma + x prefetch"}
+                 4: "fused tcgen05 + TMA, streamed gamma", 5: "fused tcgen05 + TMA, streamed gamma + x prefetch",
+                 6: "tcgen05 dx (gamma, gamma^T streamed) + split-K tcgen05 d-gamma (129-256 ch)"}
         rows = {}
         for mod, x, g, _, _ in self.sites:
             B, C = x.shape[:2]
@@ -285,13 +287,15 @@ def roofline_of_gdn(torch, mm, harness, peak_gbs, peak_src, precision):
     dbeta, dgamma = torch.empty_like(eff[0][0]), torch.empty_like(eff[0][1])
     nbytes = int(L.mmnc_gdn_backward_workspace_bytes(B, C, HW, prec))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x0.device)
+    nfw = int(L.mmnc_gdn_forward_workspace_bytes(B, C, HW, prec))  # > 0 only for the 129 .. 256 channel kernels
+    wsf = torch.empty(max(nfw, 16), dtype=torch.uint8, device=x0.device)
     idx = [0]
 
     def fwd():
         b, gm, x, _, inv = eff[idx[0] % len(eff)]
         idx[0] += 1
-        mm._lib.check(L.mmnc_gdn_forward(x.data_ptr(), B, C, HW, b.data_ptr(), gm.data_ptr(), int(inv), prec,
-                                         y.data_ptr(), st))
+        mm._lib.check(L.mmnc_gdn_forward_ws(x.data_ptr(), B, C, HW, b.data_ptr(), gm.data_ptr(), int(inv), prec,
+                                            y.data_ptr(), wsf.data_ptr(), nfw, st))
 
     def bwd():
         b, gm, x, g, inv = eff[idx[0] % len(eff)]
@@ -334,12 +338,14 @@ def roofline_of_gdn(torch, mm, harness, peak_gbs, peak_src, precision):
         yq, dbq, dgq = torch.empty_like(x), torch.empty_like(b_), torch.empty_like(gm_)
         nbq = int(L.mmnc_gdn_backward_workspace_bytes(Bq, Cq, HWq, prec))
         wsq = torch.empty(nbq, dtype=torch.uint8, device=x.device)
+        nfq = int(L.mmnc_gdn_forward_workspace_bytes(Bq, Cq, HWq, prec))
+        wfq = torch.empty(max(nfq, 16), dtype=torch.uint8, device=x.device)
         k = [0]
 
         def fq():
             k[0] += 1
-            mm._lib.check(L.mmnc_gdn_forward(xs_[k[0] & 1].data_ptr(), Bq, Cq, HWq, b_.data_ptr(), gm_.data_ptr(),
-                                             int(mod.inverse), prec, yq.data_ptr(), st))
+            mm._lib.check(L.mmnc_gdn_forward_ws(xs_[k[0] & 1].data_ptr(), Bq, Cq, HWq, b_.data_ptr(), gm_.data_ptr(),
+                                                int(mod.inverse), prec, yq.data_ptr(), wfq.data_ptr(), nfq, st))
 
         def bq():
             k[0] += 1

@@ -23,7 +23,11 @@
 // in place, sums the rows of the u box (d beta), and issues 2 (halves of the 256 output channels) x 4 (K = 8 pixels)
 // MMAs with N = 256 into a 2 x 256 column accumulator that lives in TMEM for the whole kernel.  Every CTA writes one
 // [C][C + 1] partial; gdn_reduce_partials (fixed order) adds them and applies the re-parametrisation's chain rule.
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "gdn_params.cuh"
@@ -66,41 +70,103 @@ __device__ __forceinline__ void wait_bar(uint32_t addr, uint32_t parity) {
 __device__ __forceinline__ void commit_bar(uint32_t addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
 }
+// the same arrive delivered to the barrier at this offset in every CTA of `mask` (thread-block cluster)
+__device__ __forceinline__ void commit_bar_multicast(uint32_t addr, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(addr), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void expect_bytes(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
-// The ring is driven by ONE thread (the MMA-issuing leader), whose state lives in shared memory so that it costs the
-// other 511 threads no registers.  Chunk q of the CTA's sequence goes to slot q % SLOTS; the sequence repeats the call's
-// `per_tile` chunks (gamma, then gamma^T for the backward) once per tile.
+#ifdef MMNC_WIDE_PROFILE
+__device__ unsigned long long mmnc_wide_prof[32];
+#define MMNC_TICK(i)                                                                  \
+    do {                                                                              \
+        if (threadIdx.x == 0 && blockIdx.x == 0) {                                    \
+            const long long now__ = clock64();                                        \
+            mmnc_wide_prof[i] += (unsigned long long)(now__ - tick__);                \
+            tick__ = now__;                                                           \
+        }                                                                             \
+    } while (0)
+#define MMNC_TICK_INIT() long long tick__ = clock64()
+#else
+#define MMNC_TICK(i) do { } while (0)
+#define MMNC_TICK_INIT() do { } while (0)
+#endif
+
+// The ring is driven by ONE thread per CTA (the MMA-issuing leader), whose state lives in shared memory so that it costs
+// the other 511 threads no registers.  Chunk q of the CTA's sequence goes to slot q % SLOTS; the sequence repeats the
+// call's `per_tile` chunks (gamma, then gamma^T for the backward) once per tile.
+//
+// Thread-block clusters (kCS = 2, optional): every CTA of a cluster walks the SAME chunk sequence (same number of tiles),
+// loads 1 / kCS of each chunk and MULTICASTS it into the same slot of every CTA of the cluster, so the L2 reads of gamma
+// drop by kCS.  A slot may be overwritten when all kCS consumers have released it: the "slot free" barriers count kCS
+// arrivals, and each CTA's tcgen05.commit is multicast to all of them.  (Not the default: see wide_cluster_size().)
 struct Ring {
     uint32_t base, full0, empty0;    // shared addresses: slots, "chunk landed" barriers, "slot free" barriers
     const uint32_t *packed;
     int per_tile, total;             // chunks per tile, chunks of this CTA's whole run
     int q_prod, q_cons, c;           // produced / consumed so far; position inside the per-tile sequence
     uint32_t pslot, pphase, cslot, cphase;
+    uint32_t rank;                   // of this CTA in its cluster
 };
 
-__device__ __forceinline__ void produce_one(Ring *r) {
-    const uint32_t slot = r->pslot;
-    // the MMAs that read the slot's previous occupant have retired (tcgen05.commit arrives on the barrier)
-    if (r->q_prod >= SLOTS) wait_bar(r->empty0 + 8u * slot, r->pphase ^ 1u);
-    const uint32_t bar = r->full0 + 8u * slot, dst = r->base + slot * CHUNK_BYTES;
-    const uint64_t src = reinterpret_cast<uint64_t>(r->packed) + (uint64_t)r->c * CHUNK_BYTES;
-    expect_bytes(bar, CHUNK_BYTES);
+// Every ring access below is a shared-memory round trip, and the volatile asm blocks between them keep the compiler from
+// caching anything: the first version read / wrote the struct field by field inside the chunk loop and the leader needed
+// ~1100 cycles per chunk for 4 MMAs that execute in ~500 (phase probe: the tensor pipe idled half of every contraction).
+// Now the state is copied to registers once per call, updated there, and written back at the end.
+template <int kCS>
+__device__ __forceinline__ void produce_n(Ring *r, int count) {
+    const uint32_t base = r->base, full0 = r->full0, empty0 = r->empty0, rank = r->rank;
+    const uint64_t packed = reinterpret_cast<uint64_t>(r->packed);
+    const int per_tile = r->per_tile;
+    uint32_t slot = r->pslot, phase = r->pphase;
+    int q = r->q_prod, c = r->c;
+    constexpr uint32_t SLICE = CHUNK_BYTES / kCS, PIECES = (kCS == 1) ? 4 : 2, PIECE = SLICE / PIECES;
+#pragma unroll 1
+    for (int i = 0; i < count; ++i) {
+        // the MMAs (of every CTA of the cluster) that read the slot's previous occupant have retired
+        if (q >= SLOTS) wait_bar(empty0 + 8u * slot, phase ^ 1u);
+        const uint32_t bar = full0 + 8u * slot;
+        expect_bytes(bar, CHUNK_BYTES);  // the whole chunk lands here, whoever sends the pieces
+        const uint32_t dst = base + slot * CHUNK_BYTES + rank * SLICE;
+        const uint64_t src = packed + (uint64_t)c * CHUNK_BYTES + rank * SLICE;
 #pragma unroll
-    for (uint32_t i = 0; i < 4; ++i)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst + i * (CHUNK_BYTES / 4)), "l"(src + i * (CHUNK_BYTES / 4)), "r"(CHUNK_BYTES / 4), "r"(bar)
-                     : "memory");
-    if (++r->c == r->per_tile) r->c = 0;
-    if (++r->pslot == SLOTS) { r->pslot = 0; r->pphase ^= 1u; }
-    ++r->q_prod;
+        for (uint32_t j = 0; j < PIECES; ++j) {
+            if constexpr (kCS == 1)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + j * PIECE), "l"(src + j * PIECE), "r"(PIECE), "r"(bar)
+                             : "memory");
+            else
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                             ::"r"(dst + j * PIECE), "l"(src + j * PIECE), "r"(PIECE), "r"(bar), "h"((uint16_t)((1u << kCS) - 1u))
+                             : "memory");
+        }
+        if (++c == per_tile) c = 0;
+        if (++slot == SLOTS) { slot = 0; phase ^= 1u; }
+        ++q;
+    }
+    r->pslot = slot; r->pphase = phase; r->q_prod = q; r->c = c;
 }
 
-// Fill the ring as far as it goes.  Called when every issued MMA has retired (all slots free): never blocks.
+// Fill the ring as far as it goes.  Called when every MMA this CTA has issued has retired; the other CTAs of a cluster are
+// at most one contraction behind, so a wait here is short.
+template <int kCS>
 __device__ __forceinline__ void top_up(Ring *r) {
-    while (r->q_prod < r->total && r->q_prod < r->q_cons + SLOTS) produce_one(r);
+    const int q_prod = r->q_prod;
+    int n = r->total - q_prod;
+    const int room = r->q_cons + SLOTS - q_prod;
+    if (n > room) n = room;
+    if (n > 0) produce_n<kCS>(r, n);
 }
 
 template <int KS>
@@ -114,27 +180,41 @@ __device__ __forceinline__ void chunk_mma(uint32_t d, uint32_t a, uint32_t b_lo,
 // One contraction (leader only): D[128 x 256] = A[128 x 32 n_kc] * B, chunk by chunk.  Everything already in the ring is
 // issued back to back; when the ring runs dry (n_kc > SLOTS) the remaining chunks are requested in order, each as soon as
 // the slot it reuses is released - by then the tensor pipe still has several chunks queued, which covers the L2 latency.
+template <int kCS>
 __device__ __forceinline__ void contract(uint32_t tmem_base, Ring *r, uint32_t mma_bar, int n_kc) {
-    int remaining = n_kc;
+    const uint32_t base = r->base, full0 = r->full0, empty0 = r->empty0;
+    uint32_t slot = r->cslot, phase = r->cphase;
+    int q_cons = r->q_cons, ahead = r->q_prod - q_cons;  // chunks in the ring
 #pragma unroll 1
-    for (int kc = 0; kc < n_kc; ++kc, --remaining) {
-        if (r->q_cons == r->q_prod) {
-            const int m = remaining < SLOTS ? remaining : SLOTS;
-            for (int i = 0; i < m; ++i) produce_one(r);
+    for (int kc = 0; kc < n_kc; ++kc) {
+        if (ahead == 0) {
+            const int remaining = n_kc - kc;
+            ahead = remaining < SLOTS ? remaining : SLOTS;
+            r->q_cons = q_cons;
+            produce_n<kCS>(r, ahead);
         }
-        const uint32_t slot = r->cslot;
-        wait_bar(r->full0 + 8u * slot, r->cphase);
-        chunk_mma<0>(tmem_base + P, tmem_base + (uint32_t)(kc * KC), tc::desc_lo(r->base + slot * CHUNK_BYTES, 128), kc > 0 ? 1u : 0u);
-        commit_bar(r->empty0 + 8u * slot);
-        if (++r->cslot == SLOTS) { r->cslot = 0; r->cphase ^= 1u; }
-        ++r->q_cons;
+#ifdef MMNC_WIDE_PROFILE
+        const long long w0__ = clock64();
+#endif
+        wait_bar(full0 + 8u * slot, phase);
+#ifdef MMNC_WIDE_PROFILE
+        if (blockIdx.x == 0) mmnc_wide_prof[20 + (kc < 6 ? 0 : 1)] += (unsigned long long)(clock64() - w0__);
+#endif
+        chunk_mma<0>(tmem_base + P, tmem_base + (uint32_t)(kc * KC), tc::desc_lo(base + slot * CHUNK_BYTES, 128), kc > 0 ? 1u : 0u);
+        if constexpr (kCS == 1) commit_bar(empty0 + 8u * slot);
+        else commit_bar_multicast(empty0 + 8u * slot, (uint16_t)((1u << kCS) - 1u));
+        if (++slot == SLOTS) { slot = 0; phase ^= 1u; }
+        ++q_cons;
+        --ahead;
     }
     commit_bar(mma_bar);
+    r->cslot = slot; r->cphase = phase; r->q_cons = q_cons;
 }
 
 struct Setup {
     uint32_t mma_bar, tmem_base;
-    int n_tiles;  // of this CTA
+    int n_tiles;       // of this CTA (the same for every CTA of a cluster)
+    int64_t tiles;     // of the whole call
 };
 
 }  // namespace tcw
@@ -157,17 +237,21 @@ gdn_wide_pack_kernel(const GdnParams prm, int C, int n_kc, int images, uint32_t 
     }
 }
 
-// Shared start-up of the two pixel-tile kernels.
+// Shared start-up of the two pixel-tile kernels.  Every CTA walks ceil(tiles / grid) tiles; the few indices past the end
+// are clamped to the last tile (it is computed twice, with identical results), so that the CTAs of a cluster consume
+// identical chunk sequences and the kFull instances need no per-tile predicate.
+template <int kCS>
 __device__ __forceinline__ void wide_setup(tcw::Setup &st, tcw::Ring *ring, uint8_t *smem_raw, uint64_t *bars, uint32_t *tmem_slot,
                                            float *beta_s, const GdnParams &prm, int C, int64_t NP, const uint32_t *packed,
                                            int per_tile) {
     using namespace tc;
     using namespace tcw;
-    const int64_t tiles = (NP + TILE - 1) / TILE;
-    st.n_tiles = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    st.tiles = (NP + TILE - 1) / TILE;
+    st.n_tiles = (int)((st.tiles + gridDim.x - 1) / gridDim.x);
     if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 * SLOTS + 1; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < SLOTS; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[SLOTS + i], kCS); }
+        mbar_init(&bars[2 * SLOTS], 1);
         ring->base = (smem_u32(smem_raw) + 127u) & ~127u;
         ring->full0 = smem_u32(&bars[0]);
         ring->empty0 = smem_u32(&bars[SLOTS]);
@@ -176,19 +260,24 @@ __device__ __forceinline__ void wide_setup(tcw::Setup &st, tcw::Ring *ring, uint
         ring->total = per_tile * st.n_tiles;
         ring->q_prod = ring->q_cons = ring->c = 0;
         ring->pslot = ring->pphase = ring->cslot = ring->cphase = 0u;
-        top_up(ring);  // the first chunks are on their way while the tile's x is loaded
+        ring->rank = (kCS > 1) ? cluster_rank() : 0u;
     }
     for (int i = threadIdx.x; i < P; i += THREADS) beta_s[i] = (i < C) ? prm.b(i) : 1.f;
     fence_before();
     __syncthreads();
+    if constexpr (kCS > 1) cluster_sync_all();  // every CTA's barriers exist before anyone multicasts into them
     fence_after();
+    if (threadIdx.x == 0) top_up<kCS>(ring);  // the first chunks are on their way while the tile's x is loaded
     st.mma_bar = smem_u32(&bars[2 * SLOTS]);
     st.tmem_base = *tmem_slot;
 }
 
-template <bool kInverse>
+// kFull: C = 256 and no ragged tile - every channel / pixel predicate folds away.  kHW != 0: H*W known at compile time, so
+// the channel stride turns every per-channel address into an immediate offset (otherwise one 64-bit multiply-add per
+// access: a third of the backward's instructions, measured with ncu).
+template <bool kInverse, bool kFull, int kHW, int kCS>
 __global__ void __launch_bounds__(tcw::THREADS, 1)
-gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t NP, int64_t HW, int C, const GdnParams prm,
+gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t NP, int64_t HW_rt, int C, const GdnParams prm,
                         const uint32_t *__restrict__ packed, int n_kc) {
     using namespace tc;
     using namespace tcw;
@@ -198,27 +287,31 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
     __shared__ float beta_s[P];
     __shared__ Ring ring;
     Setup st;
-    wide_setup(st, &ring, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, n_kc);
+    wide_setup<kCS>(st, &ring, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, n_kc);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {
         const int q4 = warp >> 2;                          // which 64 channels
         const int pl = ((warp & 3) << 5) | lane;           // pixel of the tile = TMEM lane
-        const int creal = min(QC, max(0, C - q4 * QC));    // real channels among this thread's 64
+        const int creal = kFull ? QC : min(QC, max(0, C - q4 * QC));    // real channels among this thread's 64
         const uint32_t lane_a = st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(q4 * QC);
         const uint32_t lane_d = lane_a + (uint32_t)P;
+        const int64_t HW = kHW ? (int64_t)kHW : HW_rt;
         const uint32_t sb = (uint32_t)HW * 4u;
         uint32_t parity = 0;
+        MMNC_TICK_INIT();
 #pragma unroll 1
         for (int t = 0; t < st.n_tiles; ++t) {
-            const int64_t pix = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE + pl;
-            const bool valid = pix < NP;
+            int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            if (tile >= st.tiles) tile = st.tiles - 1;
+            const int64_t pix = tile * TILE + pl;
+            const bool valid = kFull || pix < NP;
             const int64_t b = valid ? pix / HW : 0;
             const int64_t e0 = (b * C + q4 * QC) * HW + (valid ? pix - b * HW : 0);
             const float *xb = x + e0;
             float *yb = y + e0;
             float xv[QC];
 #pragma unroll
-            for (int c = 0; c < QC; ++c) xv[c] = (valid && c < creal) ? __ldcs(chan_ptr(xb, sb, c)) : 0.f;
+            for (int c = 0; c < QC; ++c) xv[c] = (kFull || (valid && c < creal)) ? __ldcs(chan_ptr(xb, sb, c)) : 0.f;
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += 16) {
                 uint32_t v[16];
@@ -227,16 +320,20 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
                 tmem_st16(lane_a + c0, v);
             }
             tmem_st_wait();
+            MMNC_TICK(0);
             fence_before();
             named_bar_sync(1, COMPUTE);
+            MMNC_TICK(1);
             if (threadIdx.x == 0) {
                 fence_after();
-                contract(st.tmem_base, &ring, st.mma_bar, n_kc);
+                contract<kCS>(st.tmem_base, &ring, st.mma_bar, n_kc);
             }
+            MMNC_TICK(2);
             wait_bar(st.mma_bar, parity);
+            MMNC_TICK(3);
             parity ^= 1u;
             fence_after();
-            if (threadIdx.x == 0) top_up(&ring);  // every slot is free: the next contraction's chunks land during the epilogue
+            if (threadIdx.x == 0) top_up<kCS>(&ring);  // the next contraction's chunks land during the epilogue
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += 16) {
                 uint32_t r[16];
@@ -247,26 +344,30 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
                     const float n = __uint_as_float(r[j]) + beta_s[q4 * QC + c0 + j];
                     const float rs = fast_rsqrt(n);
                     const float out = xv[c0 + j] * (kInverse ? n * rs : rs);
-                    if (valid && c0 + j < creal) __stcs(chan_ptr(yb, sb, c0 + j), out);
+                    if (kFull || (valid && c0 + j < creal)) __stcs(chan_ptr(yb, sb, c0 + j), out);
                 }
             }
+            MMNC_TICK(4);
             // every lane has drained D before the next tile's MMA overwrites it
             fence_before();
             named_bar_sync(1, COMPUTE);
             fence_after();
+            MMNC_TICK(5);
         }
     }
+    fence_before();
     __syncthreads();
+    if constexpr (kCS > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
     if (warp == 0) tmem_dealloc(st.tmem_base, 512);
 }
 
 // dx and u.  Registers: only ONE 64-channel vector stays live per thread - g, turned in place into f = g n^p by epilogue 1
 // and consumed by epilogue 2; x is read three times (A fill: HBM; the two epilogues: L2), eight channels at a time and one
 // block ahead.  g is requested while MMA1 runs.
-template <bool kInverse>
+template <bool kInverse, bool kFull, int kHW, int kCS>
 __global__ void __launch_bounds__(tcw::THREADS, 1)
 gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, float *__restrict__ dx, float *__restrict__ U,
-                   int64_t NP, int64_t HW, int C, const GdnParams prm, const uint32_t *__restrict__ packed, int n_kc) {
+                   int64_t NP, int64_t HW_rt, int C, const GdnParams prm, const uint32_t *__restrict__ packed, int n_kc) {
     using namespace tc;
     using namespace tcw;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -275,22 +376,27 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
     __shared__ float beta_s[P];
     __shared__ Ring ring;
     Setup st;
-    wide_setup(st, &ring, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, 2 * n_kc);
+    wide_setup<kCS>(st, &ring, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, 2 * n_kc);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr float coef = kInverse ? 0.5f : -0.5f;
     {
         const int q4 = warp >> 2;
         const int pl = ((warp & 3) << 5) | lane;
-        const int creal = min(QC, max(0, C - q4 * QC));
+        const int creal = kFull ? QC : min(QC, max(0, C - q4 * QC));
         const uint32_t lane_a = st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(q4 * QC);
         const uint32_t lane_d = lane_a + (uint32_t)P;
+        const int64_t HW = kHW ? (int64_t)kHW : HW_rt;
         const uint32_t sb = (uint32_t)HW * 4u;
         const float *beta_q = beta_s + q4 * QC;
         uint32_t parity = 0;
+#define MMNC_CH(c) (kFull || (valid && (c) < cr))
+        MMNC_TICK_INIT();
 #pragma unroll 1
         for (int t = 0; t < st.n_tiles; ++t) {
-            const int64_t pix = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * TILE + pl;
-            const bool valid = pix < NP;
+            int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            if (tile >= st.tiles) tile = st.tiles - 1;
+            const int64_t pix = tile * TILE + pl;
+            const bool valid = kFull || pix < NP;
             const int64_t b = valid ? pix / HW : 0;
             const int64_t e0 = (b * C + q4 * QC) * HW + (valid ? pix - b * HW : 0);
             const float *xb = x + e0, *gb = g + e0;
@@ -302,31 +408,35 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
             for (int c0 = 0; c0 < QC; c0 += 16) {
                 float xv[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) xv[j] = (valid && c0 + j < cr) ? __ldg(chan_ptr(xb, sb, c0 + j)) : 0.f;
+                for (int j = 0; j < 16; ++j) xv[j] = MMNC_CH(c0 + j) ? __ldg(chan_ptr(xb, sb, c0 + j)) : 0.f;
                 uint32_t v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = to_tf32_fast(xv[j] * xv[j]);
                 tmem_st16(lane_a + c0, v);
             }
             tmem_st_wait();
+            MMNC_TICK(8);
             fence_before();
             named_bar_sync(1, COMPUTE);
+            MMNC_TICK(9);
             if (threadIdx.x == 0) {
                 fence_after();
-                contract(st.tmem_base, &ring, st.mma_bar, n_kc);  // n - beta = x^2 gamma^T
+                contract<kCS>(st.tmem_base, &ring, st.mma_bar, n_kc);  // n - beta = x^2 gamma^T
             }
+            MMNC_TICK(10);
             // ---- g on its way while MMA1 runs
             float gf[QC];
             asm volatile("" : "+r"(cr));
 #pragma unroll
-            for (int c = 0; c < QC; ++c) gf[c] = (valid && c < cr) ? __ldcs(chan_ptr(gb, sb, c)) : 0.f;
+            for (int c = 0; c < QC; ++c) gf[c] = MMNC_CH(c) ? __ldcs(chan_ptr(gb, sb, c)) : 0.f;
             float xn[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xn[j] = (valid && j < cr) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
+            for (int j = 0; j < 8; ++j) xn[j] = MMNC_CH(j) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
             wait_bar(st.mma_bar, parity);
+            MMNC_TICK(11);
             parity ^= 1u;
             fence_after();
-            if (threadIdx.x == 0) top_up(&ring);  // every slot is free: the next contraction's chunks land during the epilogue
+            if (threadIdx.x == 0) top_up<kCS>(&ring);  // gamma^T lands during epilogue 1
             // ---- epilogue 1: u -> A and -> HBM (the d gamma kernel's operand); f = g n^p replaces g
             asm volatile("" : "+r"(cr));
 #pragma unroll
@@ -336,7 +446,7 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
                 for (int j = 0; j < 8; ++j) xc[j] = xn[j];
                 if (c0 + 8 < QC) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) xn[j] = (valid && c0 + 8 + j < cr) ? __ldg(chan_ptr(xb, sb, c0 + 8 + j)) : 0.f;
+                    for (int j = 0; j < 8; ++j) xn[j] = MMNC_CH(c0 + 8 + j) ? __ldg(chan_ptr(xb, sb, c0 + 8 + j)) : 0.f;
                 }
                 uint32_t r[8], uu[8];
                 tmem_ld8(lane_d + c0, r);
@@ -350,24 +460,28 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
                     const float gv = gf[c0 + j];
                     uu[j] = to_tf32_fast((coef * gv) * (xc[j] * pm1));  // padding channels: g = 0, so u = 0
                     gf[c0 + j] = gv * pw;
-                    if (valid && c0 + j < cr) chan_ptr(ub, sb, c0 + j)[0] = __uint_as_float(uu[j]);
+                    if (MMNC_CH(c0 + j)) chan_ptr(ub, sb, c0 + j)[0] = __uint_as_float(uu[j]);
                 }
                 tmem_st8(lane_a + c0, uu);
             }
+            MMNC_TICK(12);
             tmem_st_wait();
             fence_before();
             named_bar_sync(1, COMPUTE);
+            MMNC_TICK(13);
             if (threadIdx.x == 0) {
                 fence_after();
-                contract(st.tmem_base, &ring, st.mma_bar, n_kc);  // t = u gamma
+                contract<kCS>(st.tmem_base, &ring, st.mma_bar, n_kc);  // t = u gamma
             }
+            MMNC_TICK(14);
             asm volatile("" : "+r"(cr));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xn[j] = (valid && j < cr) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
+            for (int j = 0; j < 8; ++j) xn[j] = MMNC_CH(j) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
             wait_bar(st.mma_bar, parity);
+            MMNC_TICK(15);
             parity ^= 1u;
             fence_after();
-            if (threadIdx.x == 0) top_up(&ring);  // every slot is free: the next contraction's chunks land during the epilogue
+            if (threadIdx.x == 0) top_up<kCS>(&ring);  // the next tile's gamma lands during epilogue 2
             // ---- epilogue 2: dx = f + 2 x t
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += 8) {
@@ -376,7 +490,7 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
                 for (int j = 0; j < 8; ++j) xc[j] = xn[j];
                 if (c0 + 8 < QC) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) xn[j] = (valid && c0 + 8 + j < cr) ? __ldg(chan_ptr(xb, sb, c0 + 8 + j)) : 0.f;
+                    for (int j = 0; j < 8; ++j) xn[j] = MMNC_CH(c0 + 8 + j) ? __ldg(chan_ptr(xb, sb, c0 + 8 + j)) : 0.f;
                 }
                 uint32_t r[8];
                 tmem_ld8(lane_d + c0, r);
@@ -384,14 +498,18 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float out = fmaf(2.f * xc[j], __uint_as_float(r[j]), gf[c0 + j]);
-                    if (valid && c0 + j < cr) __stcs(chan_ptr(dxb, sb, c0 + j), out);
+                    if (MMNC_CH(c0 + j)) __stcs(chan_ptr(dxb, sb, c0 + j), out);
                 }
             }
+            MMNC_TICK(16);
             // No barrier here: the next tile's barrier (after its A fill) orders these TMEM reads of D before the next MMA1
             // overwrites it, and A was last read by MMA2, which has retired.
         }
+#undef MMNC_CH
     }
+    fence_before();
     __syncthreads();
+    if constexpr (kCS > 1) cluster_sync_all();
     if (warp == 0) tmem_dealloc(st.tmem_base, 512);
 }
 
@@ -549,6 +667,76 @@ bool gdn_tc_wide_forward_supported(int64_t B, int64_t C, int64_t HW, const void 
 
 static constexpr size_t WIDE_RING_SMEM = (size_t)tcw::SLOTS * tcw::CHUNK_BYTES + 128;
 
+// Cluster size of the pixel-tile kernels: MMNC_GDN_WIDE_CLUSTER = 1 (default) | 2.  Measured on B200 at 64 x 256 x 64 x 64:
+// forward 0.184 / 0.183 ms, backward 0.548 / 0.536 ms for 1 / 2 (and 4 was slower: 0.223 / 0.631 ms) - multicast halves the
+// L2 reads of gamma, but the contraction is bound by the shared-memory array itself (every chunk byte is written once by
+// the bulk copy and read once by the MMAs: ~130 B / clk at the full TF32 rate against 128 B / clk), not by L2.
+static int wide_cluster_size() {
+    static const int cs = []() {
+        const char *e = getenv("MMNC_GDN_WIDE_CLUSTER");
+        return (e && atoi(e) == 2) ? 2 : 1;
+    }();
+    return cs;
+}
+
+// Launch `kernel` as clusters of `cs` CTAs, as many clusters as can be resident at once (one CTA per SM).
+template <typename... Args>
+static int launch_clustered(void (*kernel)(Args...), int cs, int64_t tiles, cudaStream_t s, const char *what, Args... args) {
+    if (int rc = tmah::ensure_dynamic_smem(kernel, WIDE_RING_SMEM)) return rc;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(tcw::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = WIDE_RING_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (cs > 1) ? 1 : 0;
+    int clusters = sm_count() / cs;
+    if (cs > 1) {
+        // (kernel, cluster size, device) -> clusters that fit at once; GPCs whose SM count is not a multiple of the
+        // cluster size leave a few SMs idle
+        static std::mutex mu;
+        static std::unordered_map<uint64_t, int> cache;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(kernel) * 64u + (uint64_t)(dev & 15) * 4u + (uint64_t)(cs >> 1);
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            cfg.gridDim = dim3((unsigned)(sm_count() / cs * cs), 1, 1);
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+                cudaGetLastError();
+                n = sm_count() / cs / 2;  // conservative: half the machine
+            }
+            it = cache.emplace(key, n).first;
+        }
+        if (clusters > it->second) clusters = it->second;
+    }
+    const int64_t need = (tiles + cs - 1) / cs;
+    if (clusters > need) clusters = (int)need;
+    cfg.gridDim = dim3((unsigned)(clusters * cs), 1, 1);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    count_launch();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return MMNC_ERR_CUDA;
+    }
+    return MMNC_OK;
+}
+
+// instance tables: [inverse][shape class: 0 generic, 1 full tiles + C = 256, 2 = 1 with H*W = 1024, 3 = 1 with H*W = 4096]
+#define MMNC_WIDE_ROW(K, I, CS) { K<I, false, 0, CS>, K<I, true, 0, CS>, K<I, true, 1024, CS>, K<I, true, 4096, CS> }
+#define MMNC_WIDE_TABLE(K, CS) { MMNC_WIDE_ROW(K, false, CS), MMNC_WIDE_ROW(K, true, CS) }
+static int wide_shape_class(int64_t B, int64_t C, int64_t HW) {
+    if (C != tcw::P || (B * HW) % tcw::TILE != 0) return 0;
+    return HW == 4096 ? 3 : (HW == 1024 ? 2 : 1);
+}
+
 int gdn_tc_wide_forward(const float *x, int64_t B, int64_t C, int64_t HW, const GdnParams &prm, int inverse, float *y,
                         void *workspace, size_t workspace_bytes, cudaStream_t s) {
     MMNC_REQUIRE(gdn_tc_wide_forward_supported(B, C, HW, workspace, workspace_bytes), "gdn_tc_wide_forward: unsupported call");
@@ -557,13 +745,14 @@ int gdn_tc_wide_forward(const float *x, int64_t B, int64_t C, int64_t HW, const 
     const int elems = n_kc * tcw::KC * tcw::P;
     gdn_wide_pack_kernel<<<(elems + 255) / 256, 256, 0, s>>>(prm, (int)C, n_kc, 1, packed);
     if (int rc = after_launch("gdn_wide_pack_kernel")) return rc;
-    auto kernel = inverse ? gdn_wide_forward_kernel<true> : gdn_wide_forward_kernel<false>;
-    if (int rc = tmah::ensure_dynamic_smem(kernel, WIDE_RING_SMEM)) return rc;
+    using Kernel = void (*)(const float *, float *, int64_t, int64_t, int, const GdnParams, const uint32_t *, int);
+    static const Kernel k1[2][4] = MMNC_WIDE_TABLE(gdn_wide_forward_kernel, 1);
+    static const Kernel k2[2][4] = MMNC_WIDE_TABLE(gdn_wide_forward_kernel, 2);
+    const int cs = wide_cluster_size(), cls = wide_shape_class(B, C, HW);
+    const Kernel kernel = (cs == 1 ? k1 : k2)[inverse ? 1 : 0][cls];
     const int64_t NP = B * HW, tiles = (NP + tcw::TILE - 1) / tcw::TILE;
-    int64_t grid = sm_count();
-    if (grid > tiles) grid = tiles;
-    kernel<<<(unsigned)grid, tcw::THREADS, WIDE_RING_SMEM, s>>>(x, y, NP, HW, (int)C, prm, packed, n_kc);
-    return after_launch("gdn_wide_forward_kernel");
+    return launch_clustered(kernel, cs, tiles, s, "gdn_wide_forward_kernel", x, y, NP, HW, (int)C, prm,
+                            (const uint32_t *)packed, n_kc);
 }
 
 bool gdn_tc_wide_backward_supported(const float *x, const float *g, int64_t B, int64_t C, int64_t HW) {
@@ -593,13 +782,16 @@ int gdn_tc_wide_backward(const float *x, const float *g, int64_t B, int64_t C, i
     gdn_wide_pack_kernel<<<(elems + 255) / 256, 256, 0, s>>>(prm, (int)C, n_kc, 2, packed);
     if (int rc = after_launch("gdn_wide_pack_kernel")) return rc;
     {
-        auto kernel = inverse ? gdn_wide_dx_kernel<true> : gdn_wide_dx_kernel<false>;
-        if (int rc = tmah::ensure_dynamic_smem(kernel, WIDE_RING_SMEM)) return rc;
+        using Kernel = void (*)(const float *, const float *, float *, float *, int64_t, int64_t, int, const GdnParams,
+                                const uint32_t *, int);
+        static const Kernel k1[2][4] = MMNC_WIDE_TABLE(gdn_wide_dx_kernel, 1);
+        static const Kernel k2[2][4] = MMNC_WIDE_TABLE(gdn_wide_dx_kernel, 2);
+        const int cs = wide_cluster_size(), cls = wide_shape_class(B, C, HW);
+        const Kernel kernel = (cs == 1 ? k1 : k2)[inverse ? 1 : 0][cls];
         const int64_t NP = B * HW, tiles = (NP + tcw::TILE - 1) / tcw::TILE;
-        int64_t grid = sm_count();
-        if (grid > tiles) grid = tiles;
-        kernel<<<(unsigned)grid, tcw::THREADS, WIDE_RING_SMEM, s>>>(x, g, dx, U, NP, HW, (int)C, prm, packed, n_kc);
-        if (int rc = after_launch("gdn_wide_dx_kernel")) return rc;
+        if (int rc = launch_clustered(kernel, cs, tiles, s, "gdn_wide_dx_kernel", x, g, dx, U, NP, HW, (int)C, prm,
+                                      (const uint32_t *)packed, n_kc))
+            return rc;
     }
     CUtensorMap tm_u, tm_x;
     if (int rc = tmah::tensor_map_3d(&tm_u, U, (uint64_t)HW, (uint64_t)C, (uint64_t)B, (uint64_t)HW * 4, (uint64_t)C * HW * 4,
@@ -619,3 +811,13 @@ int gdn_tc_wide_backward(const float *x, const float *g, int64_t B, int64_t C, i
 }
 
 }  // namespace mmnc
+
+#ifdef MMNC_WIDE_PROFILE
+// tools/probes/wide_phase_probe.py: per-phase clock totals of CTA 0's leader thread (read and reset)
+extern "C" int mmnc_wide_profile_read(unsigned long long *out32) {
+    unsigned long long zero[32] = {0};
+    if (cudaMemcpyFromSymbol(out32, mmnc::tcw::mmnc_wide_prof, sizeof(zero)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(mmnc::tcw::mmnc_wide_prof, zero, sizeof(zero)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
