@@ -232,6 +232,19 @@ int mmnc_argmax_sse(const float *logits, const float *target, int64_t B, int K, 
                     float *sse, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * (f2) MS-SSIM — pytorch_msssim.ms_ssim as `average_metrics` calls it on every task (mtc.py:359-384): one SCALE per call.
+ *   x, y: (planes, H, W) fp32 (planes = B * C), both multiplied by `scale` on load (the reference scales by 255 first);
+ *   'valid' separable 11-tap Gaussian (sigma; 1.5 in the reference) over x, y, x^2, y^2, x y;
+ *   cs = (2 s12 + c2) / (s1 + s2 + c2), ssim = (2 mu1 mu2 + c1) / (mu1^2 + mu2^2 + c1) * cs;
+ *   ssim_mean, cs_mean (planes): spatial means over the (H - 10) x (W - 10) valid outputs (fixed-order reduction).
+ *   px, py (planes, H / 2, W / 2) or both NULL: the 2 x 2 average-pooled SCALED planes = the next scale's input
+ *   (H and W even; pass scale = 1 for them).  workspace: mmnc_ssim_workspace_floats(planes, H, W) floats, 8-byte aligned.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t mmnc_ssim_workspace_floats(int64_t planes, int H, int W);
+int mmnc_ssim_scale(const float *x, const float *y, int64_t planes, int H, int W, float scale, float c1, float c2,
+                    float sigma, float *workspace, float *ssim_mean, float *cs_mean, float *px, float *py, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * (f1) bias gradient of the convolutions: out[c] = sum over (b, s) of g[b, c, s] for an NCHW tensor (B, C, S).
  *   workspace: mmnc_channel_sum_workspace_floats(B, C, S) floats.  Fixed-order two-stage reduction (bit-reproducible).
  * ------------------------------------------------------------------------------------------------------- */

@@ -5,9 +5,11 @@ class-id image against the class-id target (data_range 17).  The reference evalu
 
 Here PSNR is free: the distortion kernel already reduced sum (x_hat - x)^2 / (B C), and
 PSNR = 10 log10(data_range^2 / MSE) = -10 log10(MSE of the unscaled images).  The semantic class-id image and its
-squared error come from one fused pass over the logits (`mmnc_argmax_sse`).  MS-SSIM is not on the rate path: it is
-restated with stock torch ops (separable 11-tap Gaussian filtering, 5 scales, the published weights) and can be
-thinned out with `every`; the convolutions inside it stay on cuDNN like every other convolution.
+squared error come from one fused pass over the logits (`mmnc_argmax_sse`).  MS-SSIM of CUDA tensors runs on
+`mmnc_ssim_scale` (csrc/ssim.cu): one fused launch per scale - the five Gaussian-filtered maps, the SSIM / contrast
+maps, their spatial means and the 2 x 2 pooled input of the next scale - instead of ten depth-wise convolutions and
+~20 element-wise passes (21 ms -> 1 ms for a (256, 3, 256, 256) pair).  `ms_ssim_torch` is the same computation with
+stock torch ops: what CPU tensors get, and what the kernel is tested against.
 """
 from __future__ import annotations
 
@@ -71,14 +73,59 @@ def _ssim_cs(x: Tensor, y: Tensor, win: Tensor, data_range: float):
     return ssim_map.flatten(2).mean(-1), cs_map.flatten(2).mean(-1)  # (B, C) each
 
 
-def ms_ssim(x: Tensor, y: Tensor, data_range: float = 255.0, size_average: bool = True) -> Tensor:
-    """Multi-scale SSIM as pytorch_msssim computes it: 11-tap Gaussian (sigma 1.5), 5 scales with 2x2 average pooling
-    in between, contrast-structure terms of the first four scales and the full SSIM of the last, ReLU'd, combined
-    with the published exponents, averaged over channels (and the batch)."""
+def _check_ms_ssim_args(x: Tensor, y: Tensor):
     if x.shape != y.shape or x.dim() != 4:
         raise ValueError(f"ms_ssim expects two (B, C, H, W) tensors of one shape, got {tuple(x.shape)} / {tuple(y.shape)}")
     if min(x.shape[-2:]) <= (11 - 1) * 2 ** 4:
         raise ValueError("image side must be larger than 160 for five scales with an 11-tap window")
+
+
+def _combine_scales(stack: Tensor, size_average: bool) -> Tensor:
+    """(5, B, C): relu'd contrast means of scales 0-3 and the SSIM mean of scale 4 -> the weighted product."""
+    weights = torch.tensor(MS_SSIM_WEIGHTS, dtype=stack.dtype, device=stack.device)
+    val = torch.prod(stack ** weights.view(-1, 1, 1), dim=0)
+    return val.mean() if size_average else val.mean(1)
+
+
+def ms_ssim(x: Tensor, y: Tensor, data_range: float = 255.0, size_average: bool = True, scale: float = 1.0) -> Tensor:
+    """Multi-scale SSIM as pytorch_msssim computes it: 11-tap Gaussian (sigma 1.5), 5 scales with 2x2 average pooling
+    in between, contrast-structure terms of the first four scales and the full SSIM of the last, ReLU'd, combined
+    with the published exponents, averaged over channels (and the batch).  `scale` multiplies both images first (the
+    reference compares x * 255 with data_range 255); on CUDA tensors that costs nothing (applied on load)."""
+    _check_ms_ssim_args(x, y)
+    if not (x.is_cuda and y.is_cuda):
+        return ms_ssim_torch(x * scale if scale != 1.0 else x, y * scale if scale != 1.0 else y, data_range, size_average)
+    L = _lib.lib()
+    x, y = ops._f32c(x.detach()), ops._f32c(y.detach())
+    B, C, H, W = x.shape
+    planes = B * C
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    ws = torch.empty(int(L.mmnc_ssim_workspace_floats(planes, H, W)), dtype=torch.float32, device=x.device)
+    means = torch.empty(5, 2, planes, dtype=torch.float32, device=x.device)  # [scale][ssim | cs][plane]
+    for i in range(5):
+        H, W = x.shape[-2:]
+        fused_pool = i < 4 and H % 2 == 0 and W % 2 == 0
+        px = py = None
+        if fused_pool:
+            px = torch.empty(B, C, H // 2, W // 2, dtype=torch.float32, device=x.device)
+            py = torch.empty_like(px)
+        _lib.check(L.mmnc_ssim_scale(ops._p(x), ops._p(y), planes, H, W, scale if i == 0 else 1.0, c1, c2, 1.5, ops._p(ws),
+                                     ops._p(means[i, 0]), ops._p(means[i, 1]), ops._p(px) if fused_pool else None,
+                                     ops._p(py) if fused_pool else None, ops._stream()))
+        if i < 4:
+            if fused_pool:
+                x, y = px, py
+            else:  # odd sides: pytorch_msssim pads the pooling with zeros (count_include_pad), rare enough for torch ops
+                pad = [s % 2 for s in x.shape[2:]]
+                s0 = scale if i == 0 else 1.0
+                x, y = F.avg_pool2d(x * s0, 2, padding=pad), F.avg_pool2d(y * s0, 2, padding=pad)
+    stack = torch.cat([means[:4, 1], means[4:, 0]], dim=0).view(5, B, C)
+    return _combine_scales(torch.relu(stack), size_average)
+
+
+def ms_ssim_torch(x: Tensor, y: Tensor, data_range: float = 255.0, size_average: bool = True) -> Tensor:
+    """The same computation with stock torch ops (any device)."""
+    _check_ms_ssim_args(x, y)
     win = _gaussian_window(device=x.device)
     weights = torch.tensor(MS_SSIM_WEIGHTS, dtype=x.dtype, device=x.device)
     mcs = []

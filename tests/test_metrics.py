@@ -84,3 +84,33 @@ def test_semantic_argmax_sse_kernel_and_metric_logs():
     model.train_metrics_every = 1
     model.training_step(batch)
     assert "train/rgb/psnr" in model.last_logs and "train/semantic/ms-ssim" in model.last_logs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 3, 256, 256), (3, 1, 176, 208), (1, 2, 161, 170), (5, 3, 192, 256)])
+def test_ms_ssim_kernel_against_float64_numpy_and_torch_ops(shape):
+    """mmnc_ssim_scale (one fused launch per scale, pooled next-scale input written by the same block) against the
+    independent float64 numpy implementation (2e-5 relative, the bar of the CPU test above) and against the stock-torch
+    restatement on the same device; 176 x 208: tiles that end inside the image and an 11 x 13 last scale; 161 x 170:
+    odd sides, where pytorch_msssim's zero-padded pooling is done with torch ops between the launches."""
+    rng = np.random.default_rng(5)
+    x = rng.random(shape).astype(np.float32)
+    dev = "cuda:0"
+    for noise in (0.02, 0.2):
+        y = np.clip(x + rng.standard_normal(shape).astype(np.float32) * noise, 0, 1)
+        xd, yd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
+        before = mm.launch_count()
+        got = M.ms_ssim(xd, yd, data_range=255.0, scale=255.0)
+        torch.cuda.synchronize()
+        assert mm.launch_count() - before == 10  # 5 scales x (tile kernel + fixed-order finish)
+        ref_t = M.ms_ssim_torch(xd * 255, yd * 255, data_range=255.0).item()
+        assert abs(got.item() - ref_t) <= 2e-5 * abs(ref_t), (got.item(), ref_t)
+        if shape[2] % 16 == 0 and shape[3] % 16 == 0:  # the numpy twin crops instead of padding odd sides
+            want = _ms_ssim_np(x * 255, y * 255, 255.0)
+            assert abs(got.item() - want) <= 2e-5 * abs(want), (got.item(), want)
+        per_image = M.ms_ssim(xd, yd, data_range=255.0, scale=255.0, size_average=False)
+        assert per_image.shape == (shape[0],)
+        assert torch.allclose(per_image, M.ms_ssim_torch(xd * 255, yd * 255, 255.0, size_average=False), rtol=2e-5)
+        assert torch.equal(M.ms_ssim(xd, yd, data_range=255.0, scale=255.0), got), "fixed-order reductions: bit-reproducible"
+    same = M.ms_ssim(torch.from_numpy(x).to(dev), torch.from_numpy(x).to(dev), data_range=1.0)
+    assert abs(same.item() - 1.0) < 1e-6
