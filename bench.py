@@ -508,14 +508,14 @@ def cpu_whole_step_stepper(cfg, cpu_batch: int, total_steps: int):
         ref.configure_optimizers(total_steps=max(1, total_steps))
 
         def step():
-            loss, _ = ref.training_step(batch)
+            loss, _ = ref.training_step(batch, with_metrics=True)  # PSNR + MS-SSIM of every task, like mtc.py:468
             return float(loss.detach())
     else:
         ref.eval()
 
         def step():
             with torch.no_grad():
-                loss, _ = ref.rd_loss(batch, "val")
+                loss, _ = ref.rd_loss(batch, "val", with_metrics=True)
             return float(loss)
     return step
 
@@ -541,7 +541,7 @@ def cpu_baseline_leg(cfg, cpu_batch, budget_s=20.0):
     dt2, n2 = timed(whole, 4, budget_s / 2)
     out["e2e_value"] = cpu_batch / dt2
     out["e2e_sample"] = (f"{n2} whole {'training' if cfg['mode'] == 'train' else 'validation'} steps at batch {cpu_batch} "
-                         f"(conv heads + backbone + rate path{' + both Adam steps' if cfg['mode'] == 'train' else ''}), "
+                         f"(conv heads + backbone + rate path{' + both Adam steps' if cfg['mode'] == 'train' else ''} + PSNR / MS-SSIM of every task), "
                          f"{dt2 * 1e3:.0f} ms per step")
     return out
 
@@ -822,8 +822,8 @@ def measure_config(name, args, env, steps, warmup, headline):
         res["e2e"] = {"value": world * B / t_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                       "ms_per_step": t_e2e * 1e3, "steps": n_e2e, "last_loss": last,
                       "peak_memory_GB": torch.cuda.max_memory_allocated(device) / 1e9, "layout": args.layout,
-                      "what": ("compressor.training_step(batch)" if train else
-                               "compressor.validation_step(batch) incl. PSNR + MS-SSIM of every task (the reference's validation step)") +
+                      "what": ("compressor.training_step(batch)" if train else "compressor.validation_step(batch)") +
+                              " incl. PSNR + MS-SSIM of every task (the reference logs both on every step, mtc.py:468)" +
                               ": H2D of one pinned batch per step (copy stream, prefetched one step ahead), cuDNN convs (TF32 "
                               "allowed, torch default) + mmnc kernels" +
                               (", backward, gradient all-reduce (N>1), both Adam steps" if train else "") + ", loss.item()"}

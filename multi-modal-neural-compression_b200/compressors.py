@@ -107,14 +107,14 @@ class MultiTaskCompressor(nn.Module):
         self.grad_sync = None
         self.grad_zero = None
         # step metrics (mtc.py:92, 359-384, 468): the reference evaluates PSNR and MS-SSIM of every task on EVERY step.
-        # Validation steps do the same here; training steps every `train_metrics_every` steps (0 = never, 1 = the
-        # reference's behaviour) - MS-SSIM is ~40 filtering passes per task and is not part of the loss.
+        # So does this class: `train_metrics_every` = 1 (0 = never, n = every n-th training step).  PSNR comes from the
+        # distortion sums and MS-SSIM is one fused launch per scale (csrc/ssim.cu): ~1.3 ms per step at batch 64, 3 tasks.
         # (f1) run the whole network channels-last: cuDNN's tensor-core convolutions are NHWC kernels, and with NCHW
         # tensors it converts around every one of them (~27 % of the training step's GPU time, profiles/); the GDN
         # kernels take NHWC natively for the large layers.  Switch with use_channels_last().
         self.channels_last = False
         self.metrics = ("psnr", "ms-ssim")
-        self.train_metrics_every = 0
+        self.train_metrics_every = 1
         self._train_steps = 0
 
     def get_model_name(self):

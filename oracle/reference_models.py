@@ -196,7 +196,11 @@ class ReferenceCompressor(nn.Module):
     def auxiliary_loss(self):
         return self.model["compressor"].entropy_bottleneck.loss()
 
-    def rd_loss(self, batch, log_dir="train"):
+    def average_metrics(self, x, x_hats, log_dir):                           # mtc.py:359-384
+        from . import metrics_ref
+        return metrics_ref.average_metrics(self.tasks, x, x_hats, log_dir)
+
+    def rd_loss(self, batch, log_dir="train", with_metrics=False):
         x_hats, lik = self.forward(batch)
         rec, l1 = self.multitask_reconstruction_loss(batch, x_hats, log_dir)
         comp, l2 = self.multitask_compression_loss(lik, x_hats, log_dir)
@@ -204,6 +208,10 @@ class ReferenceCompressor(nn.Module):
         logs = {f"{log_dir}/rec_loss": rec, f"{log_dir}/compression_loss": comp, f"{log_dir}/loss": loss}
         logs.update(l1)
         logs.update(l2)
+        if with_metrics:                                                      # mtc.py:468: every step, train and val
+            self._last = (batch, x_hats)
+            if log_dir != "train":
+                logs.update(self.average_metrics(batch, x_hats, log_dir))
         return loss, logs
 
     # ------------------------------------------------------------------ optimisation (mtc.py:389-466)
@@ -216,8 +224,8 @@ class ReferenceCompressor(nn.Module):
         self.sched = torch.optim.lr_scheduler.CosineAnnealingLR(self.main_opt, T_max=total_steps, eta_min=1e-8)
         self.aux_opt = torch.optim.Adam(aux, lr=self.lr_aux)
 
-    def training_step(self, batch):
-        loss, logs = self.rd_loss(batch, "train")
+    def training_step(self, batch, with_metrics=False):
+        loss, logs = self.rd_loss(batch, "train", with_metrics)
         self.main_opt.zero_grad()
         loss.backward()
         self.main_opt.step()
@@ -227,6 +235,8 @@ class ReferenceCompressor(nn.Module):
         aux.backward()
         self.aux_opt.step()
         self.sched.step()
+        if with_metrics:                                                      # after the optimiser steps, like mtc.py:468
+            logs.update(self.average_metrics(*self._last, "train"))
         return loss, logs
 
     # ------------------------------------------------------------------ eval-time coding

@@ -53,6 +53,20 @@ def test_ms_ssim_and_psnr_against_float64_numpy():
         M.ms_ssim(torch.zeros(1, 1, 128, 128), torch.zeros(1, 1, 128, 128))
 
 
+def test_oracle_metric_restatement_against_float64_numpy():
+    """oracle/metrics_ref.py (what the CPU reference arm runs and the GPU metrics are checked against) is pinned to the
+    independent float64 implementation above; PSNR to its definition."""
+    from oracle import metrics_ref
+    rng = np.random.default_rng(1)
+    x = rng.random((2, 3, 192, 224)).astype(np.float32)
+    y = np.clip(x + rng.standard_normal(x.shape).astype(np.float32) * 0.1, 0, 1)
+    got = metrics_ref.ms_ssim(torch.from_numpy(x) * 255, torch.from_numpy(y) * 255, data_range=255).item()
+    want = _ms_ssim_np(x * 255, y * 255, 255.0)
+    assert abs(got - want) <= 2e-5 * abs(want), (got, want)
+    psnr = metrics_ref.peak_signal_noise_ratio(torch.from_numpy(x) * 255, torch.from_numpy(y) * 255, 255).item()
+    assert abs(psnr - 10 * np.log10(255.0 ** 2 / (((x.astype(np.float64) - y) * 255) ** 2).mean())) < 1e-3
+
+
 @pytest.mark.gpu
 def test_semantic_argmax_sse_kernel_and_metric_logs():
     torch.manual_seed(3)
@@ -77,13 +91,18 @@ def test_semantic_argmax_sse_kernel_and_metric_logs():
     mse = ((x_hats["rgb"] - batch["rgb"]) ** 2).mean()
     assert abs(logs["val/rgb/psnr"].item() - (-10 * torch.log10(mse)).item()) < 1e-3
     assert 0.0 <= logs["val/rgb/ms-ssim"].item() <= 1.0
+    # every metric of the validation step against the oracle's restatement of torchmetrics / pytorch_msssim on the CPU
+    from oracle import metrics_ref
+    want = metrics_ref.average_metrics(tasks, {k: v.cpu() for k, v in batch.items()}, {k: v.cpu() for k, v in x_hats.items()}, "val")
+    for k, v in want.items():
+        assert abs(logs[k].item() - v.item()) <= 1e-4 * max(1.0, abs(v.item())), (k, logs[k].item(), v.item())
     model.train()
     model.configure_optimizers(total_steps=4)
-    model.training_step(batch)
-    assert not any(k.endswith("psnr") for k in model.last_logs)   # off during training unless asked for
-    model.train_metrics_every = 1
-    model.training_step(batch)
+    model.training_step(batch)   # like the reference (mtc.py:468): metrics on every training step too
     assert "train/rgb/psnr" in model.last_logs and "train/semantic/ms-ssim" in model.last_logs
+    model.train_metrics_every = 0
+    model.training_step(batch)
+    assert not any(k.endswith("psnr") for k in model.last_logs)
 
 
 @pytest.mark.gpu
