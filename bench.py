@@ -568,7 +568,7 @@ def run_reference(args):
 
     v, e = Bc / dt_rate, Bc / dt_whole
     sample = (f"each step = {what}; e2e = the whole {'training' if cfg['mode'] == 'train' else 'validation'} step (conv heads "
-              f"+ backbone + rate path + both Adam steps) at the same batch {Bc}: a bounded sample of the "
+              f"+ backbone + rate path + both Adam steps + PSNR / MS-SSIM of every task, mtc.py:468) at the same batch {Bc}: a bounded sample of the "
               f"{B}-image step of the b200 arm (CPU time per image is flat in the batch); parity unpinned")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s",

@@ -101,3 +101,40 @@ def test_wide_gdn_falls_back_when_shape_does_not_suit():
     xg = x.clone().requires_grad_(True)
     ours(xg).sum().backward()
     assert torch.isfinite(xg.grad).all()
+
+
+@pytest.mark.parametrize("shape,inverse", [((32, 256, 64, 64), True), ((64, 256, 32, 32), True), ((16, 256, 64, 64), False)])
+def test_wide_gdn_full_size_properties(shape, inverse):
+    """IGDN(256) @ 64 x 64 and @ 32 x 32 as BASELINE config C3 runs them (half / all of its batch of 64): size-independent
+    properties - odd symmetry and batch independence hold EXACTLY (the same roundings in the same order), the parameter
+    gradients of the two halves of the batch add up to the whole - and torch's own fp32 ops on the same device."""
+    torch.manual_seed(37)
+    B, C, H, W = shape
+    ours, _ = _pair(C, inverse)
+    beta, gamma = ours.beta_reparam(ours.beta).detach(), ours.gamma_reparam(ours.gamma).detach()
+    x = torch.randn(*shape, device=DEV)
+    g = torch.randn(*shape, device=DEV)
+    assert _variants(x) == (6, 6)
+
+    def run(xi, gi):
+        xr, br, gr = xi.clone().requires_grad_(True), beta.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
+        y = mm.ops.gdn(xr, br, gr, inverse, "tf32")
+        return (y.detach(),) + torch.autograd.grad(y, [xr, br, gr], gi)
+
+    y, dx, db, dg = run(x, g)
+    y2, dx2, db2, dg2 = run(-x, g)
+    assert torch.equal(y2, -y) and torch.equal(dx2, dx) and torch.equal(db2, -db) and torch.equal(dg2, -dg)
+    y3, dx3, _, _ = run(x[3:7].contiguous(), g[3:7].contiguous())
+    assert torch.equal(y3, y[3:7]) and torch.equal(dx3, dx[3:7])
+    _, _, dba, dga = run(x[: B // 2].contiguous(), g[: B // 2].contiguous())
+    _, _, dbb, dgb = run(x[B // 2:].contiguous(), g[B // 2:].contiguous())
+    assert ((dga + dgb - dg).abs().max() / dg.abs().max()).item() < 1e-5
+    assert ((dba + dbb - db).abs().max() / db.abs().max()).item() < 1e-5
+    xr, br, gr = x.clone().requires_grad_(True), beta.clone().requires_grad_(True), gamma.clone().requires_grad_(True)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        norm = torch.nn.functional.conv2d(xr * xr, gr.reshape(C, C, 1, 1), br)
+        want = xr * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+        wdx, wdb, wdg = torch.autograd.grad(want, [xr, br, gr], g)
+    assert torch.allclose(y, want.detach(), rtol=1e-3, atol=1e-4)
+    for got, ref in ((dx, wdx), (db, wdb), (dg, wdg)):
+        assert ((got - ref).abs().max() / ref.abs().max()).item() <= 2e-3

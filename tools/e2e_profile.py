@@ -31,3 +31,14 @@ tot = sum(e.self_device_time_total for e in ka)
 print("total device time per step (ms):", tot / 3 / 1e3)
 for e in rows:
     print(f"{e.self_device_time_total/3/1e3:8.3f} ms  x{e.count//3:4d}  {e.key[:110]}")
+# which operators launch the memsets (device time per step), and how many bytes' worth at ~3 TB/s
+by_op = {}
+for e in prof.events():
+    for k in getattr(e, "kernels", []) or []:
+        if "emset" in k.name:
+            d = by_op.setdefault(e.name, [0.0, 0])
+            d[0] += k.duration
+            d[1] += 1
+print("memsets by launching op:")
+for name, (dur, n) in sorted(by_op.items(), key=lambda kv: -kv[1][0])[:12]:
+    print(f"{dur/3/1e3:8.3f} ms  x{n//3:4d}  {name[:100]}")
