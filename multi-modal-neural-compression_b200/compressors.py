@@ -363,6 +363,27 @@ class MultiTaskCompressor(nn.Module):
         batch = self._as_model_format(batch)  # once: the loss reads the inputs in the same layout as the outputs
         x_hats, likelihoods = self.forward(batch)
         loss, log_dict = self.rate_distortion_loss(batch, x_hats, likelihoods, log_dir)
+        # Step metrics (mtc.py:468).  They depend only on the inputs and the reconstructions, so on a GPU they are issued
+        # NOW, on their own stream, and run underneath the backward pass instead of after the optimiser steps.  `batch` and
+        # `x_hats` stay referenced until the end of this function, where the main stream waits for the metric stream, so
+        # nothing they read can be reused early.
+        self._train_steps += 1 if is_train else 0
+        every = self.train_metrics_every if is_train else 1
+        want_metrics = bool(self.metrics) and bool(every) and (not is_train or self._train_steps % every == 0)
+        metric_logs, metric_stream = None, None
+        if want_metrics:
+            reuse = {t: log_dict[f"{log_dir}/{t}/mse"] for t in self.tasks
+                     if task_parameters[t]["loss_function"] == "mse" and f"{log_dir}/{t}/mse" in log_dict}
+            if is_train and loss.is_cuda:
+                key = ("metric_stream", str(loss.device))
+                if key not in self._cache:
+                    self._cache[key] = torch.cuda.Stream(device=loss.device)
+                metric_stream = self._cache[key]
+                metric_stream.wait_stream(torch.cuda.current_stream(loss.device))
+                with torch.cuda.stream(metric_stream):
+                    metric_logs = self.average_metrics(batch, x_hats, log_dir, reuse)
+            else:
+                metric_logs = self.average_metrics(batch, x_hats, log_dir, reuse)
         if is_train:
             main_opt, aux_opt = self.optimizers()
             if self.grad_zero is not None:
@@ -379,12 +400,10 @@ class MultiTaskCompressor(nn.Module):
             aux_loss.backward()
             aux_opt.step()
             self.lr_schedulers().step()
-            self._train_steps += 1
-        every = self.train_metrics_every if is_train else 1
-        if self.metrics and every and (not is_train or self._train_steps % every == 0):
-            reuse = {t: log_dict[f"{log_dir}/{t}/mse"] for t in self.tasks
-                     if task_parameters[t]["loss_function"] == "mse" and f"{log_dir}/{t}/mse" in log_dict}
-            log_dict.update(self.average_metrics(batch, x_hats, log_dir, reuse))
+        if metric_stream is not None:
+            torch.cuda.current_stream(loss.device).wait_stream(metric_stream)
+        if metric_logs is not None:
+            log_dict.update(metric_logs)
         self.last_logs = log_dict
         return loss
 
