@@ -243,6 +243,12 @@ int mmnc_argmax_sse(const float *logits, const float *target, int64_t B, int K, 
 size_t mmnc_ssim_workspace_floats(int64_t planes, int H, int W);
 int mmnc_ssim_scale(const float *x, const float *y, int64_t planes, int H, int W, float scale, float c1, float c2,
                     float sigma, float *workspace, float *ssim_mean, float *cs_mean, float *px, float *py, void *stream);
+/* All five scales of ms_ssim in one call (H, W multiples of 16): means [5][2][planes] = per scale the SSIM means, then
+ * the contrast means; the caller combines relu(cs_0..3) and relu(ssim_4) with the published exponents.
+ * workspace: mmnc_ms_ssim_workspace_floats(planes, H, W) floats (tile partials + the pooled planes of scales 1-4). */
+size_t mmnc_ms_ssim_workspace_floats(int64_t planes, int H, int W);
+int mmnc_ms_ssim(const float *x, const float *y, int64_t planes, int H, int W, float scale, float c1, float c2,
+                 float sigma, float *workspace, float *means, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * (f1) bias gradient of the convolutions: out[c] = sum over (b, s) of g[b, c, s] for an NCHW tensor (B, C, S).

@@ -56,6 +56,8 @@ SIGNATURES = {
     "mmnc_gdn_forward_variant": (I32, [VP, VP, I64, I64, I64, I32]),
     "mmnc_gdn_forward_raw": (I32, [VP, I64, I64, I64, VP, VP, F32, F32, F32, I32, I32, VP, VP]),
     "mmnc_ssim_workspace_floats": (ctypes.c_size_t, [I64, I32, I32]),
+    "mmnc_ms_ssim_workspace_floats": (ctypes.c_size_t, [I64, I32, I32]),
+    "mmnc_ms_ssim": (I32, [VP, VP, I64, I32, I32, F32, F32, F32, F32, VP, VP, VP]),
     "mmnc_ssim_scale": (I32, [VP, VP, I64, I32, I32, F32, F32, F32, F32, VP, VP, VP, VP, VP, VP]),
     "mmnc_gdn_forward_workspace_bytes": (ctypes.c_size_t, [I64, I64, I64, I32]),
     "mmnc_gdn_forward_ws": (I32, [VP, I64, I64, I64, VP, VP, I32, I32, VP, VP, ctypes.c_size_t, VP]),

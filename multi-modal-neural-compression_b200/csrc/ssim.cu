@@ -53,41 +53,76 @@ ssim_tile_kernel(const float *__restrict__ x, const float *__restrict__ y, int H
             pyp[o] = 0.25f * ((sy[2 * r][2 * c] + sy[2 * r][2 * c + 1]) + (sy[2 * r + 1][2 * c] + sy[2 * r + 1][2 * c + 1]));
         }
     }
-    // ---- horizontal pass of the five maps
-    for (int idx = threadIdx.x; idx < IN * T; idx += THREADS) {
-        const int r = idx / T, c = idx - r * T;
-        float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+    // ---- horizontal pass of the five maps.  Register tiling: a work item is FOUR adjacent outputs of one row - 14 loads of x
+    //      and of y (and their three products, formed once) feed 4 x 11 taps; the first version loaded 2 values per tap
+    //      and was bound by shared-memory instructions (90 per output pixel; now ~33).
+    for (int item = threadIdx.x; item < IN * (T / 4); item += THREADS) {
+        const int r = item / (T / 4), c0 = (item - r * (T / 4)) * 4;
+        float xv[K + 3], yv[K + 3];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float xv = sx[r][c + k], yv = sy[r][c + k], w = win.g[k];
-            const float wx = w * xv, wy = w * yv;
-            a += wx; b += wy;
-            aa = fmaf(wx, xv, aa); bb = fmaf(wy, yv, bb); ab = fmaf(wx, yv, ab);
+        for (int j = 0; j < K + 3; ++j) { xv[j] = sx[r][c0 + j]; yv[j] = sy[r][c0 + j]; }
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f}, aa[4] = {0.f, 0.f, 0.f, 0.f},
+              bb[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < K + 3; ++j) {
+            const float xx = xv[j] * xv[j], yy = yv[j] * yv[j], xy = xv[j] * yv[j];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int k = j - o;  // tap index of value j for output o
+                if (k >= 0 && k < K) {
+                    const float w = win.g[k];
+                    a[o] = fmaf(w, xv[j], a[o]);
+                    b[o] = fmaf(w, yv[j], b[o]);
+                    aa[o] = fmaf(w, xx, aa[o]);
+                    bb[o] = fmaf(w, yy, bb[o]);
+                    ab[o] = fmaf(w, xy, ab[o]);
+                }
+            }
         }
-        hz[0][r][c] = a; hz[1][r][c] = b; hz[2][r][c] = aa; hz[3][r][c] = bb; hz[4][r][c] = ab;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            hz[0][r][c0 + o] = a[o]; hz[1][r][c0 + o] = b[o]; hz[2][r][c0 + o] = aa[o]; hz[3][r][c0 + o] = bb[o];
+            hz[4][r][c0 + o] = ab[o];
+        }
     }
     __syncthreads();
-    // ---- vertical pass + the two maps; outputs beyond the 'valid' domain (H - 10) x (W - 10) do not count
+    // ---- vertical pass + the two maps: one thread = one column x four adjacent rows (14 loads per map for 4 x 11 taps);
+    //      outputs beyond the 'valid' domain (H - 10) x (W - 10) do not count
     float s_ssim = 0.f, s_cs = 0.f;
     const int OH = H - (K - 1), OW = W - (K - 1);
-    for (int idx = threadIdx.x; idx < T * T; idx += THREADS) {
-        const int r = idx / T, c = idx - r * T;
-        if (y0 + r >= OH || x0 + c >= OW) continue;
-        float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    static_assert(THREADS == T * (T / 4), "one vertical work item per thread");
+    {
+        const int c = threadIdx.x % T, r0 = (threadIdx.x / T) * 4;
+        float acc[5][4];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float w = win.g[k];
-            mu1 = fmaf(w, hz[0][r + k][c], mu1);
-            mu2 = fmaf(w, hz[1][r + k][c], mu2);
-            e11 = fmaf(w, hz[2][r + k][c], e11);
-            e22 = fmaf(w, hz[3][r + k][c], e22);
-            e12 = fmaf(w, hz[4][r + k][c], e12);
+        for (int m = 0; m < 5; ++m)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[m][o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < K + 3; ++j) {
+            float v[5];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) v[m] = hz[m][r0 + j][c];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int k = j - o;
+                if (k >= 0 && k < K) {
+                    const float w = win.g[k];
+#pragma unroll
+                    for (int m = 0; m < 5; ++m) acc[m][o] = fmaf(w, v[m], acc[m][o]);
+                }
+            }
         }
-        const float m11 = mu1 * mu1, m22 = mu2 * mu2, m12 = mu1 * mu2;
-        const float s1 = e11 - m11, s2 = e22 - m22, s12 = e12 - m12;
-        const float cs = (2.f * s12 + c2) / (s1 + s2 + c2);
-        s_cs += cs;
-        s_ssim += ((2.f * m12 + c1) / (m11 + m22 + c1)) * cs;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (y0 + r0 + o >= OH || x0 + c >= OW) continue;
+            const float mu1 = acc[0][o], mu2 = acc[1][o];
+            const float m11 = mu1 * mu1, m22 = mu2 * mu2, m12 = mu1 * mu2;
+            const float s1 = acc[2][o] - m11, s2 = acc[3][o] - m22, s12 = acc[4][o] - m12;
+            const float cs = (2.f * s12 + c2) / (s1 + s2 + c2);
+            s_cs += cs;
+            s_ssim += ((2.f * m12 + c1) / (m11 + m22 + c1)) * cs;
+        }
     }
     s_ssim = warp_sum(s_ssim);
     s_cs = warp_sum(s_cs);
@@ -155,3 +190,42 @@ extern "C" int mmnc_ssim_scale(const float *x, const float *y, int64_t planes, i
                                                                        1.f / ((float)OH * (float)OW), ssim_mean, cs_mean);
     return after_launch("ssim_finish_kernel");
 }
+
+// All five scales in one call (H and W multiples of 16, so that every pooling is exact 2 x 2): ten launches, no host work
+// in between.  means: [5][2][planes] = per scale the SSIM means, then the contrast means.
+// workspace: mmnc_ms_ssim_workspace_floats floats = tile partials of scale 0 + the pooled planes of scales 1 .. 4.
+extern "C" size_t mmnc_ms_ssim_workspace_floats(int64_t planes, int H, int W) {
+    if (planes <= 0 || H <= 0 || W <= 0) return 2;
+    size_t pooled = 0;
+    for (int i = 1; i < 5; ++i) pooled += 2 * (size_t)planes * (size_t)(H >> i) * (size_t)(W >> i);
+    return mmnc_ssim_workspace_floats(planes, H, W) + pooled + 8;
+}
+
+extern "C" int mmnc_ms_ssim(const float *x, const float *y, int64_t planes, int H, int W, float scale, float c1, float c2,
+                            float sigma, float *workspace, float *means, void *stream) {
+    MMNC_REQUIRE(planes >= 0 && H > 0 && W > 0, "ms_ssim: bad dimensions");
+    MMNC_REQUIRE(H % 16 == 0 && W % 16 == 0, "ms_ssim: H and W must be multiples of 16 (use mmnc_ssim_scale otherwise)");
+    MMNC_REQUIRE((H >> 4) >= ssim::K && (W >> 4) >= ssim::K, "ms_ssim: the image is too small for five scales");
+    if (planes == 0) return MMNC_OK;
+    MMNC_REQUIRE(x && y && workspace && means, "ms_ssim: null pointer");
+    size_t part = mmnc_ssim_workspace_floats(planes, H, W);
+    part = (part + 1) / 2 * 2;  // keeps the pooled planes 8-byte aligned like the partials
+    float *pool = workspace + part;
+    const float *cx = x, *cy = y;
+    for (int i = 0; i < 5; ++i) {
+        const int h = H >> i, w = W >> i;
+        float *nx = nullptr, *ny = nullptr;
+        if (i < 4) {
+            nx = pool;
+            ny = pool + (size_t)planes * (size_t)(h >> 1) * (size_t)(w >> 1);
+            pool = ny + (size_t)planes * (size_t)(h >> 1) * (size_t)(w >> 1);
+        }
+        if (int rc = mmnc_ssim_scale(cx, cy, planes, h, w, i == 0 ? scale : 1.f, c1, c2, sigma, workspace,
+                                     means + (size_t)(2 * i) * planes, means + (size_t)(2 * i + 1) * planes, nx, ny, stream))
+            return rc;
+        cx = nx;
+        cy = ny;
+    }
+    return MMNC_OK;
+}
+

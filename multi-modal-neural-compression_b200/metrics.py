@@ -80,10 +80,16 @@ def _check_ms_ssim_args(x: Tensor, y: Tensor):
         raise ValueError("image side must be larger than 160 for five scales with an 11-tap window")
 
 
+_WEIGHT_CACHE: Dict[tuple, Tensor] = {}
+
+
 def _combine_scales(stack: Tensor, size_average: bool) -> Tensor:
-    """(5, B, C): relu'd contrast means of scales 0-3 and the SSIM mean of scale 4 -> the weighted product."""
-    weights = torch.tensor(MS_SSIM_WEIGHTS, dtype=stack.dtype, device=stack.device)
-    val = torch.prod(stack ** weights.view(-1, 1, 1), dim=0)
+    """(5, B, C): relu'd contrast means of scales 0-3 and the SSIM mean of scale 4 -> prod_i stack_i ^ w_i, written as
+    exp(sum w_i ln stack_i) (0 ^ w = exp(-inf) = 0): three plain element-wise kernels, no run-time compiled pow / prod."""
+    key = (str(stack.device), stack.dtype)
+    if key not in _WEIGHT_CACHE:
+        _WEIGHT_CACHE[key] = torch.tensor(MS_SSIM_WEIGHTS, dtype=stack.dtype, device=stack.device).view(-1, 1, 1)
+    val = torch.exp((torch.log(stack) * _WEIGHT_CACHE[key]).sum(0))
     return val.mean() if size_average else val.mean(1)
 
 
@@ -100,8 +106,14 @@ def ms_ssim(x: Tensor, y: Tensor, data_range: float = 255.0, size_average: bool 
     B, C, H, W = x.shape
     planes = B * C
     c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
-    ws = torch.empty(int(L.mmnc_ssim_workspace_floats(planes, H, W)), dtype=torch.float32, device=x.device)
     means = torch.empty(5, 2, planes, dtype=torch.float32, device=x.device)  # [scale][ssim | cs][plane]
+    if H % 16 == 0 and W % 16 == 0:  # every pooling is an exact 2 x 2: all five scales in ONE call (ten launches)
+        ws = torch.empty(int(L.mmnc_ms_ssim_workspace_floats(planes, H, W)), dtype=torch.float32, device=x.device)
+        _lib.check(L.mmnc_ms_ssim(ops._p(x), ops._p(y), planes, H, W, scale, c1, c2, 1.5, ops._p(ws), ops._p(means),
+                                  ops._stream()))
+        stack = torch.cat([means[:4, 1], means[4:, 0]], dim=0).view(5, B, C)
+        return _combine_scales(torch.relu(stack), size_average)
+    ws = torch.empty(int(L.mmnc_ssim_workspace_floats(planes, H, W)), dtype=torch.float32, device=x.device)
     for i in range(5):
         H, W = x.shape[-2:]
         fused_pool = i < 4 and H % 2 == 0 and W % 2 == 0
