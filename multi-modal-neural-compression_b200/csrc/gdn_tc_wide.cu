@@ -272,7 +272,7 @@ __device__ __forceinline__ void wide_setup(tcw::Setup &st, tcw::Ring *ring, uint
     st.tmem_base = *tmem_slot;
 }
 
-// kFull: C = 256 and no ragged tile - every channel / pixel predicate folds away.  kHW != 0: H*W known at compile time, so
+// kFull: C = 192 or 256 and no ragged tile - every channel / pixel predicate folds away.  kHW != 0: H*W known at compile time, so
 // the channel stride turns every per-channel address into an immediate offset (otherwise one 64-bit multiply-add per
 // access: a third of the backward's instructions, measured with ncu).
 template <bool kInverse, bool kFull, int kHW, int kCS>
@@ -298,28 +298,41 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
         const int64_t HW = kHW ? (int64_t)kHW : HW_rt;
         const uint32_t sb = (uint32_t)HW * 4u;
         uint32_t parity = 0;
-        MMNC_TICK_INIT();
-#pragma unroll 1
-        for (int t = 0; t < st.n_tiles; ++t) {
+        // element offset of this thread's first channel in tile number t of the CTA (indices past the end: the last tile)
+        auto tile_offset = [&](int t, bool *valid) -> int64_t {
             int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
             if (tile >= st.tiles) tile = st.tiles - 1;
             const int64_t pix = tile * TILE + pl;
-            const bool valid = kFull || pix < NP;
-            const int64_t b = valid ? pix / HW : 0;
-            const int64_t e0 = (b * C + q4 * QC) * HW + (valid ? pix - b * HW : 0);
-            const float *xb = x + e0;
+            *valid = kFull || pix < NP;
+            const int64_t b = *valid ? pix / HW : 0;
+            return (b * C + q4 * QC) * HW + (*valid ? pix - b * HW : 0);
+        };
+        // x lives in registers from the A fill to the epilogue.  The epilogue hands every 16-channel block, the moment it
+        // has used it, to the NEXT tile's loads: x of tile t + 1 crosses HBM underneath the epilogue's stores, for no
+        // extra register and no extra traffic (phase probe: the A fill waited 7.7 k of a tile's 21.5 k cycles for x).
+        // kFull covers C = 192 as well as 256: a warp's 64 channels are then all real or all absent, and a warp without
+        // channels only keeps the barriers company (the MMAs never read A columns past 32 n_kc = C).
+        const bool active = !kFull || q4 * QC < C;
+        float xv[QC];
+        bool valid;
+        int64_t e0 = tile_offset(0, &valid);
+#pragma unroll
+        for (int c = 0; c < QC; ++c) xv[c] = (active && (kFull || (valid && c < creal))) ? __ldcs(chan_ptr(x + e0, sb, c)) : 0.f;
+        MMNC_TICK_INIT();
+#pragma unroll 1
+        for (int t = 0; t < st.n_tiles; ++t) {
             float *yb = y + e0;
-            float xv[QC];
+            const bool valid_t = valid;
+            if (active) {
 #pragma unroll
-            for (int c = 0; c < QC; ++c) xv[c] = (kFull || (valid && c < creal)) ? __ldcs(chan_ptr(xb, sb, c)) : 0.f;
+                for (int c0 = 0; c0 < QC; c0 += 16) {
+                    uint32_t v[16];
 #pragma unroll
-            for (int c0 = 0; c0 < QC; c0 += 16) {
-                uint32_t v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = to_tf32_fast(xv[c0 + j] * xv[c0 + j]);
-                tmem_st16(lane_a + c0, v);
+                    for (int j = 0; j < 16; ++j) v[j] = to_tf32_fast(xv[c0 + j] * xv[c0 + j]);
+                    tmem_st16(lane_a + c0, v);
+                }
+                tmem_st_wait();
             }
-            tmem_st_wait();
             MMNC_TICK(0);
             fence_before();
             named_bar_sync(1, COMPUTE);
@@ -329,6 +342,9 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
                 contract<kCS>(st.tmem_base, &ring, st.mma_bar, n_kc);
             }
             MMNC_TICK(2);
+            const bool more = t + 1 < st.n_tiles;
+            if (more) e0 = tile_offset(t + 1, &valid);
+            const float *xnext = x + e0;
             wait_bar(st.mma_bar, parity);
             MMNC_TICK(3);
             parity ^= 1u;
@@ -336,6 +352,7 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
             if (threadIdx.x == 0) top_up<kCS>(&ring);  // the next contraction's chunks land during the epilogue
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += 16) {
+                if (!active) break;
                 uint32_t r[16];
                 tmem_ld16(lane_d + c0, r);
                 tmem_ld_wait();
@@ -344,7 +361,12 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
                     const float n = __uint_as_float(r[j]) + beta_s[q4 * QC + c0 + j];
                     const float rs = fast_rsqrt(n);
                     const float out = xv[c0 + j] * (kInverse ? n * rs : rs);
-                    if (kFull || (valid && c0 + j < creal)) __stcs(chan_ptr(yb, sb, c0 + j), out);
+                    if (kFull || (valid_t && c0 + j < creal)) __stcs(chan_ptr(yb, sb, c0 + j), out);
+                }
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        xv[c0 + j] = (kFull || (valid && c0 + j < creal)) ? __ldcs(chan_ptr(xnext, sb, c0 + j)) : 0.f;
                 }
             }
             MMNC_TICK(4);
@@ -376,6 +398,9 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
     __shared__ float beta_s[P];
     __shared__ Ring ring;
     Setup st;
+#ifdef MMNC_WIDE_PROFILE
+    const long long cta_t0__ = clock64();
+#endif
     wide_setup<kCS>(st, &ring, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, 2 * n_kc);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr float coef = kInverse ? 0.5f : -0.5f;
@@ -390,6 +415,7 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
         const float *beta_q = beta_s + q4 * QC;
         uint32_t parity = 0;
 #define MMNC_CH(c) (kFull || (valid && (c) < cr))
+        const bool active = !kFull || q4 * QC < C;  // see the forward kernel
         MMNC_TICK_INIT();
 #pragma unroll 1
         for (int t = 0; t < st.n_tiles; ++t) {
@@ -403,9 +429,12 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
             float *dxb = dx + e0, *ub = U + e0;
             int cr = creal;
             asm volatile("" : "+r"(cr));  // keeps the 64 channel predicates from being hoisted out of the tile loop
-            // ---- A = x^2
+            // ---- A = x^2.  (Handing x of the next tile from epilogue 2 to this fill through registers, as the forward kernel
+            //      does, was measured: the fill drops from 7.2 k to 2.1 k cycles, but the 64 extra live values spill and
+            //      epilogue 2 goes from 8.9 k to 20.9 k - 0.55 -> 0.61 ms.)
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += 16) {
+                if (!active) break;
                 float xv[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) xv[j] = MMNC_CH(c0 + j) ? __ldg(chan_ptr(xb, sb, c0 + j)) : 0.f;
@@ -428,10 +457,10 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
             float gf[QC];
             asm volatile("" : "+r"(cr));
 #pragma unroll
-            for (int c = 0; c < QC; ++c) gf[c] = MMNC_CH(c) ? __ldcs(chan_ptr(gb, sb, c)) : 0.f;
+            for (int c = 0; c < QC; ++c) gf[c] = (active && MMNC_CH(c)) ? __ldcs(chan_ptr(gb, sb, c)) : 0.f;
             float xn[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xn[j] = MMNC_CH(j) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
+            for (int j = 0; j < 8; ++j) xn[j] = (active && MMNC_CH(j)) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
             wait_bar(st.mma_bar, parity);
             MMNC_TICK(11);
             parity ^= 1u;
@@ -441,6 +470,7 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
             asm volatile("" : "+r"(cr));
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += 8) {
+                if (!active) break;
                 float xc[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) xc[j] = xn[j];
@@ -476,15 +506,27 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
             MMNC_TICK(14);
             asm volatile("" : "+r"(cr));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xn[j] = MMNC_CH(j) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
+            for (int j = 0; j < 8; ++j) xn[j] = (active && MMNC_CH(j)) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
             wait_bar(st.mma_bar, parity);
             MMNC_TICK(15);
             parity ^= 1u;
             fence_after();
             if (threadIdx.x == 0) top_up<kCS>(&ring);  // the next tile's gamma lands during epilogue 2
-            // ---- epilogue 2: dx = f + 2 x t
+            // ---- epilogue 2: dx = f + 2 x t.  Each block also asks L2 for the same channels of the NEXT tile's x, so that the
+            //      next A fill finds them there (no register, no extra HBM traffic).
+            const float *xpf = nullptr;
+            if (kFull && active && t + 1 < st.n_tiles) {  // (the generic instances pay more for the address arithmetic than they gain)
+                int64_t tile_n = (int64_t)blockIdx.x + (int64_t)(t + 1) * gridDim.x;
+                if (tile_n >= st.tiles) tile_n = st.tiles - 1;
+                const int64_t pix_n = tile_n * TILE + pl;
+                if (kFull || pix_n < NP) {
+                    const int64_t bn = pix_n / HW;
+                    xpf = x + (bn * C + q4 * QC) * HW + (pix_n - bn * HW);
+                }
+            }
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += 8) {
+                if (!active) break;
                 float xc[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) xc[j] = xn[j];
@@ -500,6 +542,11 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
                     const float out = fmaf(2.f * xc[j], __uint_as_float(r[j]), gf[c0 + j]);
                     if (MMNC_CH(c0 + j)) __stcs(chan_ptr(dxb, sb, c0 + j), out);
                 }
+                if (xpf != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (kFull || c0 + j < cr) asm volatile("prefetch.global.L2 [%0];" ::"l"(chan_ptr(xpf, sb, c0 + j)));
+                }
             }
             MMNC_TICK(16);
             // No barrier here: the next tile's barrier (after its A fill) orders these TMEM reads of D before the next MMA1
@@ -507,6 +554,13 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
         }
 #undef MMNC_CH
     }
+#ifdef MMNC_WIDE_PROFILE
+    if (threadIdx.x == 0) {  // slowest CTA and the sum over CTAs of the dx kernel's wall cycles
+        const unsigned long long el = (unsigned long long)(clock64() - cta_t0__);
+        atomicMax(&mmnc_wide_prof[30], el);
+        atomicAdd(&mmnc_wide_prof[31], el);
+    }
+#endif
     fence_before();
     __syncthreads();
     if constexpr (kCS > 1) cluster_sync_all();
@@ -729,11 +783,11 @@ static int launch_clustered(void (*kernel)(Args...), int cs, int64_t tiles, cuda
     return MMNC_OK;
 }
 
-// instance tables: [inverse][shape class: 0 generic, 1 full tiles + C = 256, 2 = 1 with H*W = 1024, 3 = 1 with H*W = 4096]
+// instance tables: [inverse][shape class: 0 generic, 1 full tiles + C a multiple of 64, 2 = 1 with H*W = 1024, 3 = 1 with H*W = 4096]
 #define MMNC_WIDE_ROW(K, I, CS) { K<I, false, 0, CS>, K<I, true, 0, CS>, K<I, true, 1024, CS>, K<I, true, 4096, CS> }
 #define MMNC_WIDE_TABLE(K, CS) { MMNC_WIDE_ROW(K, false, CS), MMNC_WIDE_ROW(K, true, CS) }
 static int wide_shape_class(int64_t B, int64_t C, int64_t HW) {
-    if (C != tcw::P || (B * HW) % tcw::TILE != 0) return 0;
+    if (C % tcw::QC != 0 || (B * HW) % tcw::TILE != 0) return 0;  // 192 or 256 channels, no ragged tile
     return HW == 4096 ? 3 : (HW == 1024 ? 2 : 1);
 }
 
