@@ -141,6 +141,12 @@ def test_real_config_training_step_runs_and_uses_tensor_cores(name):
     assert L.mmnc_gdn_backward_variant(x.data_ptr(), x.data_ptr(), 2, c // 2, 256 * 256, auto) == 3
     x = torch.empty(2, c, 128, 128, device=DEV)
     assert L.mmnc_gdn_backward_variant(x.data_ptr(), x.data_ptr(), 2, c, 128 * 128, auto) == WIDE_VARIANT[c]
+    if name == "C3":  # the mixed-latent output heads: IGDN(2 c = 256) at 64 x 64 and 32 x 32 -> the streamed-operand kernels
+        x = torch.empty(2, 2 * c, 64, 64, device=DEV)
+        assert L.mmnc_gdn_forward_variant(x.data_ptr(), x.data_ptr(), 2, 2 * c, 64 * 64, auto) == 6
+        assert L.mmnc_gdn_backward_variant(x.data_ptr(), x.data_ptr(), 2, 2 * c, 64 * 64, auto) == 6
+        names = [type(m).__name__ + str(m.beta.numel()) for m in ours.modules() if isinstance(m, mm.GDN)]
+        assert "GDN256" in names, "config C3 should contain 256-channel IGDN layers"
 
 
 def test_real_config_actual_bits_track_estimated_bits():
