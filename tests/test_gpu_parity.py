@@ -856,7 +856,7 @@ def test_launch_counter_moves():
 # ------------------------------------------------------------------------------------------------ (f1) channels-last
 @pytest.mark.parametrize("shape", [(4, 50, 64, 64), (2, 100, 32, 32), (3, 64, 16, 16), (2, 3, 64, 64), (5, 33, 8, 8),
                                    (2, 111, 16, 16), (2, 128, 32, 32), (1, 17, 64, 64), (2, 20, 30, 31), (3, 3, 5, 7),
-                                   (2, 300, 4, 4), (3, 1, 16, 16)])
+                                   (2, 300, 4, 4), (3, 1, 16, 16), (2, 256, 64, 32), (1, 192, 64, 64)])
 @pytest.mark.parametrize("inverse", [False, True])
 def test_gdn_channels_last_matches_oracle(shape, inverse):
     """NHWC tensors through GDN (native kernels where they exist - C <= 4 streaming, 16 <= C <= 128 tensor cores with
