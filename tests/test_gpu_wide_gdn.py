@@ -138,3 +138,32 @@ def test_wide_gdn_full_size_properties(shape, inverse):
     assert torch.allclose(y, want.detach(), rtol=1e-3, atol=1e-4)
     for got, ref in ((dx, wdx), (db, wdb), (dg, wdg)):
         assert ((got - ref).abs().max() / ref.abs().max()).item() <= 2e-3
+
+
+def test_wide_gdn_cluster_multicast_path_matches_default():
+    """MMNC_GDN_WIDE_CLUSTER=2 (2-CTA clusters, gamma chunks multicast into both CTAs' rings; not the default - it measured
+    no faster) is read once per process, so it runs in a child process: same results as the default path, bit for bit."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, mmnc_b200 as mm\n"
+        "torch.manual_seed(41)\n"
+        "m = mm.GDN(256, inverse=True, precision='tf32').to('cuda:0')\n"
+        "with torch.no_grad():\n"
+        "    m.gamma.add_(torch.rand(256, 256, device='cuda:0') * 0.05)\n"
+        "x = torch.randn(5, 256, 64, 32, device='cuda:0', requires_grad=True)\n"
+        "g = torch.randn(5, 256, 64, 32, device='cuda:0')\n"
+        "y = m(x); y.backward(g)\n"
+        "torch.save([t.cpu() for t in (y.detach(), x.grad, m.beta.grad, m.gamma.grad)], __import__('sys').argv[1])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for cs in ("1", "2"):
+        path = os.path.join("/tmp", f"mmnc_wide_cluster_{cs}_{os.getpid()}.pt")
+        env = dict(os.environ, MMNC_GDN_WIDE_CLUSTER=cs, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, cwd=root, timeout=300)
+        outs.append(torch.load(path))
+        os.remove(path)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
