@@ -177,38 +177,66 @@ __device__ __forceinline__ void chunk_mma(uint32_t d, uint32_t a, uint32_t b_lo,
     }
 }
 
-// One contraction (leader only): D[128 x 256] = A[128 x 32 n_kc] * B, chunk by chunk.  Everything already in the ring is
-// issued back to back; when the ring runs dry (n_kc > SLOTS) the remaining chunks are requested in order, each as soon as
-// the slot it reuses is released - by then the tensor pipe still has several chunks queued, which covers the L2 latency.
+// One contraction (leader only): D[128 x 256] = A[128 x 32 n_kc] * B, chunk by chunk.  The ring holds at most SLOTS chunks,
+// so a contraction of more than SLOTS chunks requests its last ones on the way: one request after every issued chunk from
+// the second on - the slot it reuses belongs to a chunk whose MMAs were issued two chunks ago and have (all but) retired,
+// while the tensor pipe still has the chunks issued since then queued.  (Requesting them only when the ring ran dry, as
+// the first version did, exposed their L2 latency.  tools/probes/mma_rate_probe.cu: the tensor pipe takes 128 cycles per
+// MMA of this shape, with or without polling threads and bulk copies landing next to the operand.)
 template <int kCS>
 __device__ __forceinline__ void contract(uint32_t tmem_base, Ring *r, uint32_t mma_bar, int n_kc) {
     const uint32_t base = r->base, full0 = r->full0, empty0 = r->empty0;
     uint32_t slot = r->cslot, phase = r->cphase;
-    int q_cons = r->q_cons, ahead = r->q_prod - q_cons;  // chunks in the ring
+    int q_cons = r->q_cons, ahead = r->q_prod - q_cons;  // chunks in the ring (may include the next contraction's first)
+    int to_request = n_kc - ahead;                       // chunks of THIS contraction that are not on their way yet
+#ifdef MMNC_WIDE_PROFILE
+    long long waited__ = 0, produced__ = 0, issued__ = 0;
+#endif
 #pragma unroll 1
     for (int kc = 0; kc < n_kc; ++kc) {
-        if (ahead == 0) {
-            const int remaining = n_kc - kc;
-            ahead = remaining < SLOTS ? remaining : SLOTS;
-            r->q_cons = q_cons;
-            produce_n<kCS>(r, ahead);
+        if (ahead == 0) {  // (only when a previous top_up could not run: keeps the loop correct, not fast)
+            produce_n<kCS>(r, 1);
+            ++ahead;
+            --to_request;
         }
 #ifdef MMNC_WIDE_PROFILE
         const long long w0__ = clock64();
 #endif
         wait_bar(full0 + 8u * slot, phase);
 #ifdef MMNC_WIDE_PROFILE
-        if (blockIdx.x == 0) mmnc_wide_prof[20 + (kc < 6 ? 0 : 1)] += (unsigned long long)(clock64() - w0__);
+        waited__ += clock64() - w0__;  // (a register: a global update per chunk would sit in the issue loop itself)
+#endif
+#ifdef MMNC_WIDE_PROFILE
+        const long long i0__ = clock64();
 #endif
         chunk_mma<0>(tmem_base + P, tmem_base + (uint32_t)(kc * KC), tc::desc_lo(base + slot * CHUNK_BYTES, 128), kc > 0 ? 1u : 0u);
         if constexpr (kCS == 1) commit_bar(empty0 + 8u * slot);
         else commit_bar_multicast(empty0 + 8u * slot, (uint16_t)((1u << kCS) - 1u));
+#ifdef MMNC_WIDE_PROFILE
+        const long long i1__ = clock64();
+        issued__ += i1__ - i0__;
+#endif
         if (++slot == SLOTS) { slot = 0; phase ^= 1u; }
         ++q_cons;
         --ahead;
+        if (to_request > 0 && kc >= 1) {
+            produce_n<kCS>(r, 1);
+            ++ahead;
+            --to_request;
+#ifdef MMNC_WIDE_PROFILE
+            produced__ += clock64() - i1__;
+#endif
+        }
     }
     commit_bar(mma_bar);
     r->cslot = slot; r->cphase = phase; r->q_cons = q_cons;
+#ifdef MMNC_WIDE_PROFILE
+    if (blockIdx.x == 0) {
+        mmnc_wide_prof[20] += (unsigned long long)waited__;
+        mmnc_wide_prof[22] += (unsigned long long)produced__;
+        mmnc_wide_prof[23] += (unsigned long long)issued__;
+    }
+#endif
 }
 
 struct Setup {

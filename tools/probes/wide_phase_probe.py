@@ -75,7 +75,8 @@ def main():
             bwd = [out[i] / n for i in range(8, 17)]
             print("tiles per CTA", per_cta0)
             print("forward cycles/tile:", [round(v) for v in fwd], "sum", round(sum(fwd)))
-            print("cycles/tile waiting for chunks (fwd + 2 x dx): first six", round(out[20] / n), "last two", round(out[21] / n))
+            print("leader, cycles/tile over the forward + both dx contractions: waiting for chunks", round(out[20] / n),
+                  " requesting chunks", round(out[22] / n), " issuing MMAs + commits", round(out[23] / n))
             print("dx kernel, cycles per launch: slowest CTA (max over launches)", out[30], " mean CTA", round(out[31] / reps / min(sms, tiles)))
             print("dx      cycles/tile:", [round(v) for v in bwd], "sum", round(sum(bwd)))
 
