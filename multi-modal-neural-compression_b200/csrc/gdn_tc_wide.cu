@@ -103,70 +103,74 @@ __device__ unsigned long long mmnc_wide_prof[32];
 #define MMNC_TICK_INIT() do { } while (0)
 #endif
 
-// The ring is driven by ONE thread per CTA (the MMA-issuing leader), whose state lives in shared memory so that it costs
-// the other 511 threads no registers.  Chunk q of the CTA's sequence goes to slot q % SLOTS; the sequence repeats the
-// call's `per_tile` chunks (gamma, then gamma^T for the backward) once per tile.
+// The ring has NO shared state besides its mbarriers.  Chunk q of the CTA's sequence (the call's `per_tile` chunks - gamma,
+// then gamma^T for the backward - repeated once per tile) lives in slot q % SLOTS, and the sequence is known in advance, so
+//   * the CONSUMER (the MMA-issuing leader, thread 0) only counts: wait "landed", issue four MMAs, tcgen05.commit to "free";
+//   * every slot has its own PRODUCER: lane 0 of warp 1 + slot.  It requests the slot's next chunk whenever the slot is free
+//     and chunks remain - at start-up, and from inside every wait for a contraction (where it polls its "free" barrier next
+//     to the contraction's barrier instead of only spinning), so a slot is refilled the moment the MMAs that read it retire.
+// The first versions kept a ring descriptor in shared memory and had the leader request chunks: ~660 cycles per request on
+// the very thread that feeds the tensor pipe (128 cycles per MMA when nothing starves it, tools/probes/mma_rate_probe.cu),
+// and six requests in a row at the top of its epilogue with 511 threads waiting for it at the next barrier.
 //
 // Thread-block clusters (kCS = 2, optional): every CTA of a cluster walks the SAME chunk sequence (same number of tiles),
-// loads 1 / kCS of each chunk and MULTICASTS it into the same slot of every CTA of the cluster, so the L2 reads of gamma
-// drop by kCS.  A slot may be overwritten when all kCS consumers have released it: the "slot free" barriers count kCS
-// arrivals, and each CTA's tcgen05.commit is multicast to all of them.  (Not the default: see wide_cluster_size().)
-struct Ring {
-    uint32_t base, full0, empty0;    // shared addresses: slots, "chunk landed" barriers, "slot free" barriers
-    const uint32_t *packed;
-    int per_tile, total;             // chunks per tile, chunks of this CTA's whole run
-    int q_prod, q_cons, c;           // produced / consumed so far; position inside the per-tile sequence
-    uint32_t pslot, pphase, cslot, cphase;
-    uint32_t rank;                   // of this CTA in its cluster
-};
+// each producer loads 1 / kCS of its chunk and MULTICASTS it into the same slot of every CTA of the cluster, so the L2
+// reads of gamma drop by kCS.  A slot may be overwritten when all kCS consumers have released it: the "free" barriers
+// count kCS arrivals, and each CTA's tcgen05.commit is multicast to all of them.  (Not the default: wide_cluster_size().)
+struct RingAddr { uint32_t base, full0, empty0; };  // shared addresses: slots, "chunk landed" barriers, "slot free" barriers
 
-// Every ring access below is a shared-memory round trip, and the volatile asm blocks between them keep the compiler from
-// caching anything: the first version read / wrote the struct field by field inside the chunk loop and the leader needed
-// ~1100 cycles per chunk for 4 MMAs that execute in ~500 (phase probe: the tensor pipe idled half of every contraction).
-// Now the state is copied to registers once per call, updated there, and written back at the end.
-template <int kCS>
-__device__ __forceinline__ void produce_n(Ring *r, int count) {
-    const uint32_t base = r->base, full0 = r->full0, empty0 = r->empty0, rank = r->rank;
-    const uint64_t packed = reinterpret_cast<uint64_t>(r->packed);
-    const int per_tile = r->per_tile;
-    uint32_t slot = r->pslot, phase = r->pphase;
-    int q = r->q_prod, c = r->c;
-    constexpr uint32_t SLICE = CHUNK_BYTES / kCS, PIECES = (kCS == 1) ? 4 : 2, PIECE = SLICE / PIECES;
-#pragma unroll 1
-    for (int i = 0; i < count; ++i) {
-        // the MMAs (of every CTA of the cluster) that read the slot's previous occupant have retired
-        if (q >= SLOTS) wait_bar(empty0 + 8u * slot, phase ^ 1u);
-        const uint32_t bar = full0 + 8u * slot;
-        expect_bytes(bar, CHUNK_BYTES);  // the whole chunk lands here, whoever sends the pieces
-        const uint32_t dst = base + slot * CHUNK_BYTES + rank * SLICE;
-        const uint64_t src = packed + (uint64_t)c * CHUNK_BYTES + rank * SLICE;
-#pragma unroll
-        for (uint32_t j = 0; j < PIECES; ++j) {
-            if constexpr (kCS == 1)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst + j * PIECE), "l"(src + j * PIECE), "r"(PIECE), "r"(bar)
-                             : "memory");
-            else
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                             ::"r"(dst + j * PIECE), "l"(src + j * PIECE), "r"(PIECE), "r"(bar), "h"((uint16_t)((1u << kCS) - 1u))
-                             : "memory");
-        }
-        if (++c == per_tile) c = 0;
-        if (++slot == SLOTS) { slot = 0; phase ^= 1u; }
-        ++q;
-    }
-    r->pslot = slot; r->pphase = phase; r->q_prod = q; r->c = c;
+__device__ __forceinline__ bool test_bar(uint32_t addr, uint32_t parity) {  // non-blocking
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 
-// Fill the ring as far as it goes.  Called when every MMA this CTA has issued has retired; the other CTAs of a cluster are
-// at most one contraction behind, so a wait here is short.
+// Producer of slot `slot`: request its chunk number `round` (CTA chunk q = round * SLOTS + slot) if the slot is free.
 template <int kCS>
-__device__ __forceinline__ void top_up(Ring *r) {
-    const int q_prod = r->q_prod;
-    int n = r->total - q_prod;
-    const int room = r->q_cons + SLOTS - q_prod;
-    if (n > room) n = room;
-    if (n > 0) produce_n<kCS>(r, n);
+__device__ __forceinline__ bool try_produce(const RingAddr &ra, int slot, int &round, int total, int per_tile,
+                                            const uint32_t *packed, uint32_t rank) {
+    const int q = round * SLOTS + slot;
+    if (q >= total) return false;
+    // the MMAs (of every CTA of the cluster) that read the slot's previous occupant have retired
+    if (round > 0 && !test_bar(ra.empty0 + 8u * (uint32_t)slot, (uint32_t)((round - 1) & 1))) return false;
+    const int c = q % per_tile;
+    const uint32_t bar = ra.full0 + 8u * (uint32_t)slot;
+    expect_bytes(bar, CHUNK_BYTES);  // the whole chunk lands here, whoever sends the pieces
+    constexpr uint32_t SLICE = CHUNK_BYTES / kCS, PIECES = (kCS == 1) ? 4 : 2, PIECE = SLICE / PIECES;
+    const uint32_t dst = ra.base + (uint32_t)slot * CHUNK_BYTES + rank * SLICE;
+    const uint64_t src = reinterpret_cast<uint64_t>(packed) + (uint64_t)c * CHUNK_BYTES + rank * SLICE;
+#pragma unroll
+    for (uint32_t j = 0; j < PIECES; ++j) {
+        if constexpr (kCS == 1)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + j * PIECE), "l"(src + j * PIECE), "r"(PIECE), "r"(bar)
+                         : "memory");
+        else
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                         ::"r"(dst + j * PIECE), "l"(src + j * PIECE), "r"(PIECE), "r"(bar), "h"((uint16_t)((1u << kCS) - 1u))
+                         : "memory");
+    }
+    ++round;
+    return true;
+}
+
+// Every thread's wait for a contraction; the slot producers keep their slots filled while they wait.  When the
+// contraction's barrier completes, every chunk it read has been released, so one more attempt refills the slot.
+template <int kCS>
+__device__ __forceinline__ void wait_contraction(uint32_t mma_bar, uint32_t parity, const RingAddr &ra, int my_slot, int &round,
+                                                 int total, int per_tile, const uint32_t *packed, uint32_t rank) {
+    if (my_slot < 0) {
+        wait_bar(mma_bar, parity);
+        return;
+    }
+    while (!test_bar(mma_bar, parity)) try_produce<kCS>(ra, my_slot, round, total, per_tile, packed, rank);
+    try_produce<kCS>(ra, my_slot, round, total, per_tile, packed, rank);
 }
 
 template <int KS>
@@ -177,65 +181,31 @@ __device__ __forceinline__ void chunk_mma(uint32_t d, uint32_t a, uint32_t b_lo,
     }
 }
 
-// One contraction (leader only): D[128 x 256] = A[128 x 32 n_kc] * B, chunk by chunk.  The ring holds at most SLOTS chunks,
-// so a contraction of more than SLOTS chunks requests its last ones on the way: one request after every issued chunk from
-// the second on - the slot it reuses belongs to a chunk whose MMAs were issued two chunks ago and have (all but) retired,
-// while the tensor pipe still has the chunks issued since then queued.  (Requesting them only when the ring ran dry, as
-// the first version did, exposed their L2 latency.  tools/probes/mma_rate_probe.cu: the tensor pipe takes 128 cycles per
-// MMA of this shape, with or without polling threads and bulk copies landing next to the operand.)
+// One contraction (leader only): D[128 x 256] = A[128 x 32 n_kc] * B, chunk by chunk.  q_cons = chunks consumed so far.
 template <int kCS>
-__device__ __forceinline__ void contract(uint32_t tmem_base, Ring *r, uint32_t mma_bar, int n_kc) {
-    const uint32_t base = r->base, full0 = r->full0, empty0 = r->empty0;
-    uint32_t slot = r->cslot, phase = r->cphase;
-    int q_cons = r->q_cons, ahead = r->q_prod - q_cons;  // chunks in the ring (may include the next contraction's first)
-    int to_request = n_kc - ahead;                       // chunks of THIS contraction that are not on their way yet
+__device__ __forceinline__ void contract(uint32_t tmem_base, const RingAddr &ra, uint32_t mma_bar, int n_kc, int &q_cons) {
+    uint32_t slot = (uint32_t)(q_cons % SLOTS), phase = (uint32_t)((q_cons / SLOTS) & 1);
 #ifdef MMNC_WIDE_PROFILE
-    long long waited__ = 0, produced__ = 0, issued__ = 0;
+    long long waited__ = 0;
 #endif
 #pragma unroll 1
     for (int kc = 0; kc < n_kc; ++kc) {
-        if (ahead == 0) {  // (only when a previous top_up could not run: keeps the loop correct, not fast)
-            produce_n<kCS>(r, 1);
-            ++ahead;
-            --to_request;
-        }
 #ifdef MMNC_WIDE_PROFILE
         const long long w0__ = clock64();
 #endif
-        wait_bar(full0 + 8u * slot, phase);
+        wait_bar(ra.full0 + 8u * slot, phase);
 #ifdef MMNC_WIDE_PROFILE
         waited__ += clock64() - w0__;  // (a register: a global update per chunk would sit in the issue loop itself)
 #endif
-#ifdef MMNC_WIDE_PROFILE
-        const long long i0__ = clock64();
-#endif
-        chunk_mma<0>(tmem_base + P, tmem_base + (uint32_t)(kc * KC), tc::desc_lo(base + slot * CHUNK_BYTES, 128), kc > 0 ? 1u : 0u);
-        if constexpr (kCS == 1) commit_bar(empty0 + 8u * slot);
-        else commit_bar_multicast(empty0 + 8u * slot, (uint16_t)((1u << kCS) - 1u));
-#ifdef MMNC_WIDE_PROFILE
-        const long long i1__ = clock64();
-        issued__ += i1__ - i0__;
-#endif
+        chunk_mma<0>(tmem_base + P, tmem_base + (uint32_t)(kc * KC), tc::desc_lo(ra.base + slot * CHUNK_BYTES, 128), kc > 0 ? 1u : 0u);
+        if constexpr (kCS == 1) commit_bar(ra.empty0 + 8u * slot);
+        else commit_bar_multicast(ra.empty0 + 8u * slot, (uint16_t)((1u << kCS) - 1u));
         if (++slot == SLOTS) { slot = 0; phase ^= 1u; }
-        ++q_cons;
-        --ahead;
-        if (to_request > 0 && kc >= 1) {
-            produce_n<kCS>(r, 1);
-            ++ahead;
-            --to_request;
-#ifdef MMNC_WIDE_PROFILE
-            produced__ += clock64() - i1__;
-#endif
-        }
     }
     commit_bar(mma_bar);
-    r->cslot = slot; r->cphase = phase; r->q_cons = q_cons;
+    q_cons += n_kc;
 #ifdef MMNC_WIDE_PROFILE
-    if (blockIdx.x == 0) {
-        mmnc_wide_prof[20] += (unsigned long long)waited__;
-        mmnc_wide_prof[22] += (unsigned long long)produced__;
-        mmnc_wide_prof[23] += (unsigned long long)issued__;
-    }
+    if (blockIdx.x == 0) mmnc_wide_prof[20] += (unsigned long long)waited__;
 #endif
 }
 
@@ -243,6 +213,11 @@ struct Setup {
     uint32_t mma_bar, tmem_base;
     int n_tiles;       // of this CTA (the same for every CTA of a cluster)
     int64_t tiles;     // of the whole call
+    RingAddr ra;
+    int my_slot;       // the ring slot this thread produces for, or -1
+    int round;         // chunks this producer has requested
+    int total;         // chunks of this CTA's whole run
+    uint32_t rank;     // of this CTA in its cluster
 };
 
 }  // namespace tcw
@@ -269,33 +244,32 @@ gdn_wide_pack_kernel(const GdnParams prm, int C, int n_kc, int images, uint32_t 
 // are clamped to the last tile (it is computed twice, with identical results), so that the CTAs of a cluster consume
 // identical chunk sequences and the kFull instances need no per-tile predicate.
 template <int kCS>
-__device__ __forceinline__ void wide_setup(tcw::Setup &st, tcw::Ring *ring, uint8_t *smem_raw, uint64_t *bars, uint32_t *tmem_slot,
-                                           float *beta_s, const GdnParams &prm, int C, int64_t NP, const uint32_t *packed,
-                                           int per_tile) {
+__device__ __forceinline__ void wide_setup(tcw::Setup &st, uint8_t *smem_raw, uint64_t *bars, uint32_t *tmem_slot, float *beta_s,
+                                           const GdnParams &prm, int C, int64_t NP, const uint32_t *packed, int per_tile) {
     using namespace tc;
     using namespace tcw;
     st.tiles = (NP + TILE - 1) / TILE;
     st.n_tiles = (int)((st.tiles + gridDim.x - 1) / gridDim.x);
-    if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 512);
+    st.total = per_tile * st.n_tiles;
+    st.ra.base = (smem_u32(smem_raw) + 127u) & ~127u;
+    st.ra.full0 = smem_u32(&bars[0]);
+    st.ra.empty0 = smem_u32(&bars[SLOTS]);
+    st.rank = (kCS > 1) ? cluster_rank() : 0u;
+    const int warp = threadIdx.x >> 5;
+    st.my_slot = ((threadIdx.x & 31) == 0 && warp >= 1 && warp <= SLOTS) ? warp - 1 : -1;
+    st.round = 0;
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (threadIdx.x == 0) {
         for (int i = 0; i < SLOTS; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[SLOTS + i], kCS); }
         mbar_init(&bars[2 * SLOTS], 1);
-        ring->base = (smem_u32(smem_raw) + 127u) & ~127u;
-        ring->full0 = smem_u32(&bars[0]);
-        ring->empty0 = smem_u32(&bars[SLOTS]);
-        ring->packed = packed;
-        ring->per_tile = per_tile;
-        ring->total = per_tile * st.n_tiles;
-        ring->q_prod = ring->q_cons = ring->c = 0;
-        ring->pslot = ring->pphase = ring->cslot = ring->cphase = 0u;
-        ring->rank = (kCS > 1) ? cluster_rank() : 0u;
     }
     for (int i = threadIdx.x; i < P; i += THREADS) beta_s[i] = (i < C) ? prm.b(i) : 1.f;
     fence_before();
     __syncthreads();
     if constexpr (kCS > 1) cluster_sync_all();  // every CTA's barriers exist before anyone multicasts into them
     fence_after();
-    if (threadIdx.x == 0) top_up<kCS>(ring);  // the first chunks are on their way while the tile's x is loaded
+    // the first chunks are on their way while the tile's x is loaded
+    if (st.my_slot >= 0) try_produce<kCS>(st.ra, st.my_slot, st.round, st.total, per_tile, packed, st.rank);
     st.mma_bar = smem_u32(&bars[2 * SLOTS]);
     st.tmem_base = *tmem_slot;
 }
@@ -313,9 +287,9 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
     __shared__ uint64_t bars[2 * SLOTS + 1];
     __shared__ uint32_t tmem_slot;
     __shared__ float beta_s[P];
-    __shared__ Ring ring;
     Setup st;
-    wide_setup<kCS>(st, &ring, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, n_kc);
+    wide_setup<kCS>(st, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, n_kc);
+    int q_cons = 0;  // (leader) chunks consumed
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     {
         const int q4 = warp >> 2;                          // which 64 channels
@@ -367,17 +341,16 @@ gdn_wide_forward_kernel(const float *__restrict__ x, float *__restrict__ y, int6
             MMNC_TICK(1);
             if (threadIdx.x == 0) {
                 fence_after();
-                contract<kCS>(st.tmem_base, &ring, st.mma_bar, n_kc);
+                contract<kCS>(st.tmem_base, st.ra, st.mma_bar, n_kc, q_cons);
             }
             MMNC_TICK(2);
             const bool more = t + 1 < st.n_tiles;
             if (more) e0 = tile_offset(t + 1, &valid);
             const float *xnext = x + e0;
-            wait_bar(st.mma_bar, parity);
+            wait_contraction<kCS>(st.mma_bar, parity, st.ra, st.my_slot, st.round, st.total, n_kc, packed, st.rank);
             MMNC_TICK(3);
             parity ^= 1u;
             fence_after();
-            if (threadIdx.x == 0) top_up<kCS>(&ring);  // the next contraction's chunks land during the epilogue
 #pragma unroll
             for (int c0 = 0; c0 < QC; c0 += 16) {
                 if (!active) break;
@@ -424,12 +397,12 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
     __shared__ uint64_t bars[2 * SLOTS + 1];
     __shared__ uint32_t tmem_slot;
     __shared__ float beta_s[P];
-    __shared__ Ring ring;
     Setup st;
 #ifdef MMNC_WIDE_PROFILE
     const long long cta_t0__ = clock64();
 #endif
-    wide_setup<kCS>(st, &ring, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, 2 * n_kc);
+    wide_setup<kCS>(st, smem_raw, bars, &tmem_slot, beta_s, prm, C, NP, packed, 2 * n_kc);
+    int q_cons = 0;  // (leader) chunks consumed
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr float coef = kInverse ? 0.5f : -0.5f;
     {
@@ -478,7 +451,7 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
             MMNC_TICK(9);
             if (threadIdx.x == 0) {
                 fence_after();
-                contract<kCS>(st.tmem_base, &ring, st.mma_bar, n_kc);  // n - beta = x^2 gamma^T
+                contract<kCS>(st.tmem_base, st.ra, st.mma_bar, n_kc, q_cons);  // n - beta = x^2 gamma^T
             }
             MMNC_TICK(10);
             // ---- g on its way while MMA1 runs
@@ -489,11 +462,10 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
             float xn[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) xn[j] = (active && MMNC_CH(j)) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
-            wait_bar(st.mma_bar, parity);
+            wait_contraction<kCS>(st.mma_bar, parity, st.ra, st.my_slot, st.round, st.total, 2 * n_kc, packed, st.rank);
             MMNC_TICK(11);
             parity ^= 1u;
             fence_after();
-            if (threadIdx.x == 0) top_up<kCS>(&ring);  // gamma^T lands during epilogue 1
             // ---- epilogue 1: u -> A and -> HBM (the d gamma kernel's operand); f = g n^p replaces g
             asm volatile("" : "+r"(cr));
 #pragma unroll
@@ -529,17 +501,16 @@ gdn_wide_dx_kernel(const float *__restrict__ x, const float *__restrict__ g, flo
             MMNC_TICK(13);
             if (threadIdx.x == 0) {
                 fence_after();
-                contract<kCS>(st.tmem_base, &ring, st.mma_bar, n_kc);  // t = u gamma
+                contract<kCS>(st.tmem_base, st.ra, st.mma_bar, n_kc, q_cons);  // t = u gamma
             }
             MMNC_TICK(14);
             asm volatile("" : "+r"(cr));
 #pragma unroll
             for (int j = 0; j < 8; ++j) xn[j] = (active && MMNC_CH(j)) ? __ldg(chan_ptr(xb, sb, j)) : 0.f;
-            wait_bar(st.mma_bar, parity);
+            wait_contraction<kCS>(st.mma_bar, parity, st.ra, st.my_slot, st.round, st.total, 2 * n_kc, packed, st.rank);
             MMNC_TICK(15);
             parity ^= 1u;
             fence_after();
-            if (threadIdx.x == 0) top_up<kCS>(&ring);  // the next tile's gamma lands during epilogue 2
             // ---- epilogue 2: dx = f + 2 x t.  Each block also asks L2 for the same channels of the NEXT tile's x, so that the
             //      next A fill finds them there (no register, no extra HBM traffic).
             const float *xpf = nullptr;
