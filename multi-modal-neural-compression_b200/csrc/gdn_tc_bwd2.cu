@@ -242,6 +242,11 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     const int pix = tg & 127;
     const int c_begin = (tg >> 7) * KH;
     const bool leader = (tg == 0);
+    // The asynchronous refills are issued by OTHER threads than the one that issues the MMAs: each costs its thread a few
+    // hundred cycles (context reads from shared memory, coordinates, four to eight bulk / TMA instructions), the whole
+    // group waits at the next barrier for its slowest thread, and the MMA issuer is on the critical path anyway.
+    const bool loader_b = kStream ? (tg == 32) : false;              // gamma / gamma^T buffer
+    const bool loader_t = DEFER ? leader : (tg == 64);               // landing stages (the deferred refill lives in the leader's MMA1 block)
     const uint32_t bar_id = 1u + (uint32_t)group;
     const uint32_t tmem_base = tmem_base_in;
     const uint32_t a_base = tmem_base + (uint32_t)(group * 2 * P);
@@ -332,7 +337,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         parity ^= 1;
         fence_after();
         // MMA1 has retired: the buffer it read is refilled with gamma^T while epilogue 1 runs
-        if (kStream && leader) bwd2_load_b<P>(t, 1);
+        if (loader_b) bwd2_load_b<P>(t, 1);
         // ---- epilogue 1: u -> A (TMEM) and over g in the landing buffer (MMA3's A operand); f = g n^p kept for later
         MMNC_FRESH_OI();
 #pragma unroll
@@ -384,7 +389,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         fence_after();
         // MMA2 has retired: gamma comes back for the next tile's MMA1 while epilogue 2 runs (nothing is left in flight
         // when the CTA has no further tile)
-        if (kStream && leader && k + NGROUPS < t.n_k) bwd2_load_b<P>(t, 0);
+        if (loader_b && k + NGROUPS < t.n_k) bwd2_load_b<P>(t, 0);
         // ---- epilogue 2: dx = g n^p + 2 x t
         bool refilled = false;
         {
@@ -409,7 +414,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
                 }
                 // single stage: the next tile's load can only start when MMA3 has retired, and every cycle until then
                 // is exposed - poll between the blocks of this epilogue instead of finishing it first
-                if (NSTAGES == 1 && leader && !refilled && mbar_test_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1))) {
+                if (NSTAGES == 1 && loader_t && !refilled && mbar_test_addr(fbar, (uint32_t)(((k - group) / NGROUPS) & 1))) {
                     if constexpr (kXPF) bwd2_refill_xpf(t, k);
                     else if (k + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, k + NSTAGES);
                     refilled = true;
@@ -420,7 +425,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         // of this tile before the next MMA1 overwrites D, and A was last read by MMA2, which has completed.
         // The stage is free once MMA3 (its last reader) has retired: refill it with the tile NSTAGES ahead, now or
         // (DEFER) while the group waits for the next tile's MMA1.
-        if (leader) {
+        if (loader_t) {
             if (DEFER) {
                 pending = k;
             } else if (!refilled) {
@@ -436,7 +441,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         mbar_wait_addr(fbar, (uint32_t)(((pending - group) / NGROUPS) & 1));
         if (pending + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, pending + NSTAGES);
     }
-    // the leader has seen the last MMA3 retire; after this barrier D3 is final for the whole group
+    // the refilling thread has seen the last MMA3 retire; after this barrier D3 is final for the whole group
     fence_before();
     named_bar_sync(bar_id, TPG);
     fence_after();
