@@ -246,7 +246,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
     // hundred cycles (context reads from shared memory, coordinates, four to eight bulk / TMA instructions), the whole
     // group waits at the next barrier for its slowest thread, and the MMA issuer is on the critical path anyway.
     const bool loader_b = kStream ? (tg == 32) : false;              // gamma / gamma^T buffer
-    const bool loader_t = DEFER ? leader : (tg == 64);               // landing stages (the deferred refill lives in the leader's MMA1 block)
+    const bool loader_t = (tg == 64);                                // landing stages
     const uint32_t bar_id = 1u + (uint32_t)group;
     const uint32_t tmem_base = tmem_base_in;
     const uint32_t a_base = tmem_base + (uint32_t)(group * 2 * P);
@@ -318,13 +318,13 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
             if constexpr (kStream) mbar_wait_addr(t.bfull, 0u);  // fills alternate gamma (phase 0) / gamma^T (phase 1)
             mma_ts_chain<0, P / 8>(a_base + P, a_base, desc_lo(t.gamma0, 128), GAMMA_HI, IDESC);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-            // A refill that could not be issued at the end of the previous tile (its MMA3 had not retired yet) is
-            // issued here, while the whole group waits for MMA1 anyway.
-            if (DEFER && pending >= 0) {
-                mbar_wait_addr(fbar, (uint32_t)(((pending - group) / NGROUPS) & 1));
-                if (pending + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, pending + NSTAGES);
-                pending = -1;
-            }
+        }
+        // A refill that could not be issued at the end of the previous tile (its MMA3 had not retired yet) is issued
+        // here, while the whole group waits for MMA1 anyway.
+        if (DEFER && loader_t && pending >= 0) {
+            mbar_wait_addr(fbar, (uint32_t)(((pending - group) / NGROUPS) & 1));
+            if (pending + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, pending + NSTAGES);
+            pending = -1;
         }
         // g has had the A fill and the MMA1 issue to land behind x
         mbar_wait_addr(bar_g, gpar);
@@ -437,7 +437,7 @@ __device__ __forceinline__ bool bwd2_group_loop(const volatile Bwd2Ctx &t, int g
         first = false;
     }
     // the last tile of the group: wait for its MMA3 (D3 is final after that) and hand its stage on if anyone needs it
-    if (DEFER && leader && pending >= 0) {
+    if (DEFER && loader_t && pending >= 0) {
         mbar_wait_addr(fbar, (uint32_t)(((pending - group) / NGROUPS) & 1));
         if (pending + NSTAGES < t.n_k) bwd2_issue_tile<NSTAGES>(t, pending + NSTAGES);
     }
